@@ -1,0 +1,145 @@
+"""Seeded synthetic inputs for the global-reconstruction path.
+
+There is no network in the build/bench environment and the SMPL body model is licence-gated, so every test
+and benchmark runs on assets generated here.  Three generators:
+
+* ``make_smpl_assets``   -- an SMPL-shaped body model (6890 vertices, 24 joints, 10 betas, 207 pose features)
+* ``make_pose_dict``     -- one person's HybrIK-shaped ``pose_dict`` (layout written by the reference's
+                            ``pose_est/hybrik_demo/demo.py:348-354`` and consumed at
+                            ``global_recon/models/global_recon_model.py:88-125``)
+* ``make_in_dict``       -- the ``in_dict`` handed to ``GlobalReconOptimizer.optimize`` (``run_demo.py:78-79``)
+
+Everything is numpy on the host: this is data generation, not the product's compute path.
+"""
+import numpy as np
+from scipy.spatial.transform import Rotation
+
+NUM_VERTS = 6890
+NUM_JOINTS = 24
+NUM_BETAS = 10
+NUM_POSE_FEAT = 207
+
+# standard SMPL kinematic tree (kintree_table[0] of the model file)
+SMPL_PARENTS = np.array([-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21],
+                        dtype=np.int64)
+
+# smplx VertexJointSelector picks appended after the 24 LBS joints (nose, eyes, ears, feet, then fingertips)
+EXTRA_VERTEX_IDS = np.array([332, 6260, 2800, 4071, 583, 3216, 3226, 3387, 6617, 6624, 6787,
+                             2746, 2319, 2445, 2556, 2673, 6191, 5782, 5905, 6016, 6133], dtype=np.int64)
+
+# index into [24 LBS | 21 picks | 9 extra-regressed] for the 26 'body26fk' joints
+# (reference lib/models/smpl.py:35-57 JOINT_MAP composed with :221-250)
+BODY26FK_JOINT_MAP = np.array([49, 1, 2, 51, 4, 5, 12, 7, 8, 29, 32, 30, 33, 31, 34, 24, 26, 25, 28, 27,
+                               16, 17, 18, 19, 20, 21], dtype=np.int64)
+
+# (body26fk index, SMPL joint index) pairs that share a joint name (global_recon_model.py:82-85)
+SMPL_TO_BODY26FK = np.array([[0, 0], [1, 1], [2, 2], [4, 4], [5, 5], [6, 12], [7, 7], [8, 8],
+                             [20, 16], [21, 17], [22, 18], [23, 19], [24, 20], [25, 21]], dtype=np.int64)
+
+
+def make_smpl_assets(seed=0, skin_nnz=4, reg_nnz=8):
+    """SMPL-shaped constants with the sparsity pattern of the real model (<=4 skin weights per vertex,
+    a handful of vertices per regressor row), stored dense like the reference stores them."""
+    rng = np.random.default_rng(seed)
+    a = {}
+    a['v_template'] = rng.normal(0.0, 0.3, (NUM_VERTS, 3)).astype(np.float32)
+    a['shapedirs'] = rng.normal(0.0, 0.01, (NUM_VERTS, 3, NUM_BETAS)).astype(np.float32)
+    a['posedirs'] = rng.normal(0.0, 0.001, (NUM_POSE_FEAT, NUM_VERTS * 3)).astype(np.float32)
+    w = np.zeros((NUM_VERTS, NUM_JOINTS), np.float32)
+    for v in range(NUM_VERTS):
+        js = rng.choice(NUM_JOINTS, skin_nnz, replace=False)
+        w[v, js] = rng.dirichlet(np.ones(skin_nnz)).astype(np.float32)
+    a['lbs_weights'] = w
+
+    def regressor(rows):
+        r = np.zeros((rows, NUM_VERTS), np.float32)
+        for i in range(rows):
+            vs = rng.choice(NUM_VERTS, reg_nnz, replace=False)
+            r[i, vs] = rng.dirichlet(np.ones(reg_nnz)).astype(np.float32)
+        return r
+    a['J_regressor'] = regressor(NUM_JOINTS)
+    a['J_regressor_extra'] = regressor(9)
+    a['parents'] = SMPL_PARENTS.copy()
+    a['faces'] = rng.integers(0, NUM_VERTS, (13776, 3)).astype(np.int64)
+    return a
+
+
+def _rodrigues_np(aa):
+    return Rotation.from_rotvec(aa.reshape(-1, 3)).as_matrix().reshape(aa.shape[:-1] + (3, 3))
+
+
+def fk_joints_np(assets, pose_aa, betas):
+    """24 posed LBS joints (rooted at the SMPL pelvis) for data generation only."""
+    T = pose_aa.shape[0]
+    v_shaped = assets['v_template'][None] + np.einsum('bl,mkl->bmk', betas, assets['shapedirs'])
+    J = np.einsum('bik,ji->bjk', v_shaped, assets['J_regressor'])
+    R = _rodrigues_np(pose_aa.reshape(T, 24, 3))
+    parents = assets['parents']
+    G_R = np.zeros((T, 24, 3, 3))
+    G_t = np.zeros((T, 24, 3))
+    G_R[:, 0] = R[:, 0]
+    G_t[:, 0] = J[:, 0]
+    for k in range(1, 24):
+        p = parents[k]
+        G_R[:, k] = G_R[:, p] @ R[:, k]
+        G_t[:, k] = np.einsum('bij,bj->bi', G_R[:, p], J[:, k] - J[:, p]) + G_t[:, p]
+    return G_t - G_t[:, [0]]
+
+
+def make_pose_dict(assets, person, num_fr, seed=0, exist=None, kp_noise_px=2.0):
+    """HybrIK-shaped estimates for one person.  Arrays hold VISIBLE frames only."""
+    rng = np.random.default_rng(1000 * (seed + 1) + person)
+    T = num_fr
+    base = rng.normal(0.0, 0.2, (1, 24, 3))
+    aa = base + np.cumsum(rng.normal(0.0, 0.01, (T, 24, 3)), axis=0)
+    aa[:, 0] = np.array([np.pi, 0.0, 0.0]) + rng.normal(0.0, 0.05, (1, 3)) + np.cumsum(rng.normal(0.0, 0.005, (T, 3)), axis=0)
+    betas = np.repeat(rng.normal(0.0, 0.5, (1, NUM_BETAS)), T, axis=0) + rng.normal(0.0, 0.01, (T, NUM_BETAS))
+    root_trans = np.array([0.8 * person, 0.2, 5.0]) + np.cumsum(rng.normal(0.0, 0.01, (T, 3)), axis=0)
+    cam_K = np.tile(np.array([[1000.0, 0.0, 960.0], [0.0, 1000.0, 540.0], [0.0, 0.0, 1.0]]), (T, 1, 1))
+
+    joints = fk_joints_np(assets, aa.reshape(T, 72), betas) + root_trans[:, None]
+    proj = np.einsum('bij,bkj->bki', cam_K, joints)
+    kp24 = proj[..., :2] / proj[..., 2:]
+    kp_2d = np.zeros((T, 29, 2))
+    kp_2d[:, :24] = kp24 + rng.normal(0.0, kp_noise_px, kp24.shape)
+    kp_2d[:, 24:] = kp24[:, :5]
+
+    rotmats = _rodrigues_np(aa)                      # live reference code reads 24 rotation matrices
+    if exist is None:
+        exist = np.ones(T)
+    exist = np.asarray(exist, dtype=np.float64)
+    vis = exist == 1
+    return {
+        'smpl_pose_quat_wroot': rotmats.reshape(T, 54, 4).astype(np.float32)[vis],
+        'smpl_beta': betas.astype(np.float32)[vis],
+        'root_trans': root_trans.astype(np.float32)[vis],
+        'kp_2d': kp_2d.astype(np.float32)[vis],
+        'cam_K': cam_K.astype(np.float32)[vis],
+        'frames': np.where(vis)[0],
+        'frame2ind': {int(f): i for i, f in enumerate(np.where(vis)[0])},
+        'bboxes_dict': {'id': person, 'exist': exist, 'start': int(np.where(vis)[0][0]),
+                        'end': int(np.where(vis)[0][-1]), 'num_frames': int(vis.sum()),
+                        'exist_frames': np.where(vis)[0]},
+    }
+
+
+def make_exist_with_gaps(num_fr, seed=0, n_gaps=2, min_len=10, max_len=60):
+    """3DPW-like visibility: a few runs of invisible frames, never frame 0."""
+    rng = np.random.default_rng(seed + 77)
+    exist = np.ones(num_fr)
+    for _ in range(n_gaps):
+        ln = int(rng.integers(min_len, max_len + 1))
+        ln = min(ln, max(1, num_fr // 4))
+        s = int(rng.integers(11, max(12, num_fr - ln - 1)))
+        exist[s:s + ln] = 0
+    exist[0] = 1
+    exist[-1] = 1
+    return exist
+
+
+def make_in_dict(assets, num_persons, num_fr, seed=0, gaps=False, seq_name='synthetic'):
+    est = {}
+    for p in range(num_persons):
+        exist = make_exist_with_gaps(num_fr, seed=seed * 31 + p) if gaps else None
+        est[p] = make_pose_dict(assets, p, num_fr, seed=seed, exist=exist)
+    return {'est': est, 'gt': {}, 'gt_meta': {}, 'seq_name': seq_name}
