@@ -1,0 +1,40 @@
+"""Shared test helpers: golden-fixture loading and a learned-prior stub that replays recorded outputs."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+GLOBALOPT_CASES = ['dynamic_p1_t40', 'static_p1_t24', 'static_multi_p3_t30', 'dynamic_multi_p2_t32', '3dpw_p2_t80_gaps']
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False))
+
+
+class ReplayMT:
+    """Stands in for MotionTrajJointModel: returns, call by call, what the reference's (seeded random-init)
+    infiller + trajectory predictor produced when the fixture was generated."""
+
+    def __init__(self, gold, device='cpu'):
+        self.gold, self.calls, self.device = gold, 0, device
+
+    def inference(self, batch, sample_num=1):
+        i = self.calls
+        self.calls += 1
+        return {k: torch.tensor(self.gold[f'mt/{i}/{k}'], device=self.device) for k in
+                ['infer_out_body_pose', 'infer_out_local_traj_tp', 'infer_out_orient', 'infer_out_trans']}
+
+
+def case_setup(name, smpl_assets):
+    """-> (gold dict, Config with the fixture's iteration count, in_dict)"""
+    from glamr_b200.config import Config
+    from glamr_b200.synthetic import make_in_dict
+    gold = load_golden('globalopt_' + name)
+    P, T, gaps, niters = [int(v) for v in gold['meta']]
+    cfg = Config(str(gold['cfg_id']))
+    for st in cfg.opt_stage_specs.values():
+        st['opt_niters'] = niters
+    in_dict = make_in_dict(smpl_assets, P, T, seed=0, gaps=bool(gaps), seq_name=name)
+    return gold, cfg, in_dict

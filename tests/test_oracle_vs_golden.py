@@ -1,0 +1,114 @@
+"""Pin the oracle (oracle/) against outputs of the executed reference stored in tests/golden/ (CPU only)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GLOBALOPT_CASES, ReplayMT, case_setup, load_golden
+from oracle import rotations as rt
+from oracle import traj_codec as tc
+from oracle.global_opt import OracleGlobalRecon
+from oracle.smpl import OracleSMPL
+
+
+def _t(x):
+    return torch.tensor(x)
+
+
+def test_rotation_functions_match_reference():
+    g = load_golden('rotations')
+    aa, d6, R, q, qn, q2, y, x = [_t(g[k]) for k in ['in_aa', 'in_d6', 'in_R', 'in_q', 'in_qn', 'in_q2', 'in_y', 'in_x']]
+    M = rt.make_transform(aa, d6[:, :3], 'axis_angle')
+    got = {
+        'aa_to_rotmat': rt.aa_to_rotmat(aa), 'rotmat_to_quat': rt.rotmat_to_quat(R), 'quat_to_aa': rt.quat_to_aa(qn),
+        'quat_to_aa_raw': rt.quat_to_aa(q), 'aa_to_quat': rt.aa_to_quat(aa), 'quat_to_rotmat': rt.quat_to_rotmat(q),
+        'rotmat_to_aa': rt.rotmat_to_aa(R), 'quat_mul': rt.quat_mul(qn, q2), 'quat_angle_diff': rt.quat_angle_diff(qn, q2),
+        'safe_atan2': rt.safe_atan2(y, x), 'rot6d_to_rotmat': rt.rot6d_to_rotmat(d6), 'aa_to_rot6d': rt.aa_to_rot6d(aa),
+        'rot6d_to_quat': rt.rot6d_to_quat(d6), 'get_heading': rt.get_heading(qn), 'get_heading_q': rt.get_heading_q(qn),
+        'heading_to_quat': rt.heading_to_quat(y), 'deheading_quat': rt.deheading_quat(qn),
+        'make_transform_aa': M, 'inverse_transform': rt.inverse_transform(M),
+        'transform_rot': rt.transform_rot(M, aa.flip(0)), 'transform_trans': rt.transform_trans(M, d6[:, 3:]),
+    }
+    for k, v in got.items():
+        np.testing.assert_allclose(v.numpy(), g[k], rtol=0, atol=2e-6, err_msg=k)
+    # the reference's own docstring known answer (konia_transform.py:492-497)
+    np.testing.assert_allclose(rt.quat_to_rotmat(torch.tensor([0., 0., 0., 1.])).numpy(), np.diag([-1., -1., 1.]), atol=1e-7)
+    np.testing.assert_allclose(g['doc_quat_to_rotmat'], np.diag([-1., -1., 1.]), atol=1e-7)
+
+
+def test_traj_codec_matches_reference():
+    g = load_golden('traj_codec')
+    local = _t(g['in_local'])
+    trans, q = tc.local_to_global(local)
+    np.testing.assert_allclose(trans.numpy(), g['trans'], atol=2e-6)
+    np.testing.assert_allclose(q.numpy(), g['orient_q'], atol=2e-6)
+    np.testing.assert_allclose(rt.quat_to_aa(q).numpy(), g['orient_aa'], atol=5e-6)
+    np.testing.assert_allclose(tc.global_to_local(trans, q).numpy(), g['global_to_local'], atol=5e-6)
+    vis = _t(g['in_vis'])
+    np.testing.assert_allclose(tc.interp_orient_q_sep_heading(q[vis], vis).numpy(), g['interp_q'], atol=5e-6)
+
+
+def test_smpl_matches_reference(smpl_assets):
+    g = load_golden('smpl')
+    smpl = OracleSMPL(smpl_assets)
+    o, p, b, t, s = [_t(g[k]) for k in ['in_orient', 'in_pose', 'in_betas', 'in_trans', 'in_scale']]
+    vsel = g['vsel']
+    j, v = smpl(o, p, b, root_trans=t)
+    np.testing.assert_allclose(j.numpy(), g['joints'], atol=2e-6)
+    np.testing.assert_allclose(v[:, vsel].numpy(), g['verts_sel'], atol=2e-6)
+    np.testing.assert_allclose(v.double().sum(1).numpy(), g['verts_sum'], atol=2e-3)
+    np.testing.assert_allclose(v.double().abs().sum(1).numpy(), g['verts_abs_sum'], rtol=1e-6)
+    j, v = smpl(o, p, b, root_trans=t, root_scale=s)
+    np.testing.assert_allclose(j.numpy(), g['joints_scaled'], atol=2e-6)
+    np.testing.assert_allclose(v[:, vsel].numpy(), g['verts_scaled_sel'], atol=2e-6)
+    j, v = smpl(o, p, b)
+    np.testing.assert_allclose(j.numpy(), g['joints_raw'], atol=2e-6)
+    np.testing.assert_allclose(v[:, vsel].numpy(), g['verts_raw_sel'], atol=2e-6)
+    j, v = smpl(o, p, b, root_trans=t, orig_joints=True)
+    np.testing.assert_allclose(j.numpy(), g['joints24'], atol=2e-6)
+    np.testing.assert_allclose(v[:, vsel].numpy(), g['verts24_sel'], atol=2e-6)
+    np.testing.assert_allclose(smpl.get_joints(o, p, root_trans=t).numpy(), g['fk_joints'], atol=2e-6)
+
+
+@pytest.mark.parametrize('name', GLOBALOPT_CASES)
+def test_globalopt_trajectory_matches_reference(name, smpl_assets):
+    """init state, iteration-0 gradients of every stage, per-iteration residuals and the final variables."""
+    gold, cfg, in_dict = case_setup(name, smpl_assets)
+    model = OracleGlobalRecon(cfg, smpl_assets, mt_model=ReplayMT(gold))
+    data = model.init_data(in_dict)
+    for pid, pd in data['person_data'].items():
+        for k in ['kp_2d_pred', 'smpl_orient_world', 'root_trans_world', 'traj_local_pred']:
+            tol = 1e-3 if k == 'kp_2d_pred' else 1e-5
+            np.testing.assert_allclose(pd[k].numpy(), gold[f'init/{pid}/{k}'], atol=tol, err_msg=f'init {pid} {k}')
+    np.testing.assert_allclose(data['cam_pose'].numpy(), gold['init/cam_pose'], atol=1e-5)
+    for stage, specs in cfg.opt_stage_specs.items():
+        logs = []
+        grads0 = {}
+        params = model.get_parameter(data, specs['opt_variables'])
+
+        def on_iter(it, last, dt):
+            logs.append({k: float(v) for k, v in last['uw'].items()})
+            if it == 0:
+                for i, p in enumerate(params):
+                    grads0[i] = None if p.grad is None else p.grad.detach().clone().numpy()
+        # get_parameter is idempotent w.r.t. tensors already created; optimize_main calls it again
+        orig = model.get_parameter
+        model.get_parameter = lambda d, v: params
+        model.optimize_main(data, specs['opt_variables'], specs['opt_lr'], specs['opt_niters'], specs['loss_cfg'],
+                            {'stage': stage}, on_iter)
+        model.get_parameter = orig
+        for i in range(len(params)):
+            ref = gold[f'grad0/{stage}/{i}']
+            if ref.size == 0:
+                assert grads0[i] is None or not np.any(grads0[i])
+                continue
+            scale = max(np.abs(ref).max(), 1e-12)
+            assert np.abs(grads0[i] - ref).max() / scale < 2e-4, f'grad {stage} param {i}'
+        for k in logs[0]:
+            ref = gold[f'loss/{stage}/{k}']
+            got = np.array([l[k] for l in logs])
+            np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-6, err_msg=f'{stage} {k}')
+    for pid, pd in data['person_data'].items():
+        for k in ['smpl_orient_world', 'root_trans_world', 'traj_local_xy', 'traj_local_rot', 'world_dheading']:
+            if f'final/{pid}/{k}' in gold:
+                np.testing.assert_allclose(pd[k].detach().numpy(), gold[f'final/{pid}/{k}'], atol=1e-4, err_msg=f'final {pid} {k}')
+    np.testing.assert_allclose(data['cam_pose'].numpy(), gold['final/cam_pose'], atol=1e-4)
