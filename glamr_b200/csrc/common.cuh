@@ -1,0 +1,76 @@
+// Shared device/host helpers for the glamr_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/glamr_b200.h"
+
+#define GLAMR_CUDA_TRY(expr)                       \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+#define GLAMR_LAUNCH_CHECK()                       \
+  do {                                             \
+    cudaError_t _e = cudaGetLastError();           \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+namespace glamr {
+
+constexpr int kV = GLAMR_NUM_VERTS;          // 6890
+constexpr int kNJ = GLAMR_NUM_JOINTS;        // 24
+constexpr int kNB = GLAMR_NUM_BETAS;         // 10
+constexpr int kPF = GLAMR_NUM_POSE_FEAT;     // 207
+constexpr int kPFPad = 208;                  // row stride of the pose-feature scratch
+constexpr int kVTile = 128;                  // vertices per LBS CTA
+constexpr int kNVTiles = (kV + kVTile - 1) / kVTile;   // 54
+constexpr int kVPad = kNVTiles * kVTile;     // 6912
+constexpr int kTileCols = kVTile * 3;        // 384 posedirs columns per tile
+constexpr int kChunkK = 9;                   // pose-feature rows per pipeline stage (= one joint's 3x3)
+constexpr int kNChunks = kPF / kChunkK;      // 23
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk) wrappers -------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+// global -> shared bulk copy through the TMA engine; completion is signalled on `bar` (complete_tx::bytes).
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace glamr

@@ -1,0 +1,582 @@
+// SMPL forward on sm_100a: Rodrigues + kinematic chain (pose_prep), blend shapes + pose blend + linear blend skinning
+// (lbs_kernel: 1-D bulk-TMA / mbarrier double-buffered posedirs slabs, FP32 FMA, K-sparse skinning), extra joint
+// regression + joint remap + re-rooting (joints_finalize).  Reference arithmetic: smplx.lbs as stated in-tree at
+// HybrIK/hybrik/models/layers/smpl/lbs.py:195-288,402-548 and GLAMR's wrapper lib/models/smpl.py:289-343.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "glamr_math.cuh"
+#include "smpl_model.cuh"
+
+namespace glamr {
+
+// ------------------------------------------------------------------------------------------------ pose_prep
+// One warp per frame-person, lane j < 24 owns joint j.
+//   R_j = rodrigues(pose_j)                                   lbs.py:446-477
+//   J_j = j_template + j_shapedirs . beta  (== J_regressor @ v_shaped, lbs.py:240-244, by linearity)
+//   G_j = G_parent(j) * [R_j | J_j - J_parent],  A_j = G_j - [0 | G_j J_j]      lbs.py:493-548
+__global__ void __launch_bounds__(128) pose_prep_kernel(SmplDev m, int n, const float* __restrict__ orient,
+                                                        const float* __restrict__ body_pose,
+                                                        const float* __restrict__ betas, int use_betas, SmplWorkspace w) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (f >= n) return;
+  const int j = lane < kNJ ? lane : kNJ - 1;
+  float r[3];
+  if (j == 0) {
+    r[0] = orient ? orient[f * 3 + 0] : 0.0f;
+    r[1] = orient ? orient[f * 3 + 1] : 0.0f;
+    r[2] = orient ? orient[f * 3 + 2] : 0.0f;
+  } else {
+    const float* bp = body_pose + (size_t)f * 69 + (j - 1) * 3;
+    r[0] = bp[0]; r[1] = bp[1]; r[2] = bp[2];
+  }
+  float R[9];
+  rodrigues_smplx(r, R);
+  float J[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = m.j_template[j * 3 + c];
+    if (use_betas) {
+      const float* js = m.j_shapedirs + (j * 3 + c) * kNB;
+      const float* b = betas + (size_t)f * kNB;
+#pragma unroll
+      for (int l = 0; l < kNB; ++l) v = fmaf(js[l], b[l], v);
+    }
+    J[c] = v;
+  }
+  if (lane >= 1 && lane < kNJ) {
+    float* pf = w.pf + (size_t)f * kPFPad + (lane - 1) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pf[k] = R[k] - ((k % 4 == 0) ? 1.0f : 0.0f);
+  }
+  if (lane == 0) w.pf[(size_t)f * kPFPad + kPF] = 0.0f;
+
+  float GR[9], Gt[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) GR[k] = R[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) Gt[k] = J[k];
+  const int par = m.parents[j] < 0 ? 0 : m.parents[j];
+  const int lev = m.level[j];
+  for (int l = 1; l < m.n_levels; ++l) {
+    float pR[9], pt[3], pJ[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pR[k] = __shfl_sync(0xffffffffu, GR[k], par);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pt[k] = __shfl_sync(0xffffffffu, Gt[k], par);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pJ[k] = __shfl_sync(0xffffffffu, J[k], par);
+    if (lev == l) {
+      float nR[9], rel[3], nt[3];
+      mat3_mul(pR, R, nR);
+      rel[0] = J[0] - pJ[0]; rel[1] = J[1] - pJ[1]; rel[2] = J[2] - pJ[2];
+      mat3_vec(pR, rel, nt);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) GR[k] = nR[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Gt[k] = nt[k] + pt[k];
+    }
+  }
+  if (lane < kNJ) {
+    float* jp = w.jposed + ((size_t)f * kNJ + j) * 3;
+    jp[0] = Gt[0]; jp[1] = Gt[1]; jp[2] = Gt[2];
+    float GJ[3];
+    mat3_vec(GR, J, GJ);
+    float* A = w.A + ((size_t)f * kNJ + j) * 12;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      A[i * 4 + 0] = GR[i * 3 + 0];
+      A[i * 4 + 1] = GR[i * 3 + 1];
+      A[i * 4 + 2] = GR[i * 3 + 2];
+      A[i * 4 + 3] = Gt[i] - GJ[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ lbs_kernel
+// CTA = 128 vertices x 32 frame-persons, 256 threads: thread = 1 vertex x 16 frames (48 FP32 accumulators).
+//   v_posed = v_template + shapedirs.beta + posedirs^T.pose_feature           lbs.py:240,256-267
+//   vert    = (sum_k w_k A_k) [v_posed; 1]                                    lbs.py:273-284
+// The CTA's posedirs slab [207][384] is streamed L2 -> shared memory in 23 chunks of 9 rows (13,824 B contiguous
+// each, thanks to the tile-major re-layout) by the TMA engine (cp.async.bulk + mbarrier), double buffered.
+constexpr int kFramesPerCta = 32;
+constexpr int kFramesPerThread = 16;
+constexpr int kLbsThreads = 256;
+constexpr int kChunkFloats = kChunkK * kTileCols;                 // 3456
+constexpr uint32_t kChunkBytes = kChunkFloats * sizeof(float);    // 13,824
+constexpr int kLbsSmemFloats = 2 * kChunkFloats + 2 * kChunkK * kFramesPerCta + kFramesPerCta * kNJ * 12 + kFramesPerCta * kNB;
+constexpr size_t kLbsSmemBytes = kLbsSmemFloats * sizeof(float) + 2 * sizeof(uint64_t);
+
+template <int KREG>
+__global__ void __launch_bounds__(kLbsThreads, 2)
+lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, SmplWorkspace w, float* __restrict__ vertices) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* PDs = reinterpret_cast<float*>(smem_raw);              // [2][9][384]
+  float* pfs = PDs + 2 * kChunkFloats;                           // [2][9][32]
+  float* As = pfs + 2 * kChunkK * kFramesPerCta;                 // [32][24][12]
+  float* bs = As + kFramesPerCta * kNJ * 12;                     // [32][10]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bs + kFramesPerCta * kNB);
+
+  const int tid = threadIdx.x;
+  const int vl = tid & (kVTile - 1);
+  const int fg = tid >> 7;
+  const int vtile = blockIdx.x;
+  const int f0 = n_begin + blockIdx.y * kFramesPerCta;
+  const int gv = vtile * kVTile + vl;
+  const float* pd_slab = m.pd_tiles + (size_t)vtile * kPF * kTileCols;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], kChunkBytes);
+    tma_bulk_g2s(PDs, pd_slab, kChunkBytes, &bars[0]);
+  }
+  for (int e = tid; e < kFramesPerCta * kNJ * 12; e += kLbsThreads) {
+    const int f = e / (kNJ * 12), r = e - f * (kNJ * 12);
+    const int n = f0 + f;
+    As[e] = (n < n_end) ? w.A[(size_t)n * kNJ * 12 + r] : 0.0f;
+  }
+  for (int e = tid; e < kFramesPerCta * kNB; e += kLbsThreads) {
+    const int f = e / kNB, l = e - f * kNB;
+    const int n = f0 + f;
+    bs[e] = (n < n_end) ? betas[(size_t)n * kNB + l] : 0.0f;
+  }
+  auto load_pf_chunk = [&](int c, int s) {
+    for (int e = tid; e < kChunkK * kFramesPerCta; e += kLbsThreads) {
+      const int f = e / kChunkK, k = e - f * kChunkK;
+      const int n = f0 + f;
+      pfs[s * kChunkK * kFramesPerCta + k * kFramesPerCta + f] = (n < n_end) ? w.pf[(size_t)n * kPFPad + c * kChunkK + k] : 0.0f;
+    }
+  };
+  load_pf_chunk(0, 0);
+
+  float acc[kFramesPerThread][3];
+  {
+    float sdv[30];
+    const float* sd = m.shapedirs + (size_t)gv * 30;
+#pragma unroll
+    for (int k = 0; k < 30; ++k) sdv[k] = sd[k];
+    const float vt0 = m.v_template[gv * 3 + 0], vt1 = m.v_template[gv * 3 + 1], vt2 = m.v_template[gv * 3 + 2];
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < kFramesPerThread; ++f) {
+      const float* b = bs + (fg * kFramesPerThread + f) * kNB;
+      float a0 = vt0, a1 = vt1, a2 = vt2;
+#pragma unroll
+      for (int l = 0; l < kNB; ++l) {
+        const float bl = b[l];
+        a0 = fmaf(sdv[l], bl, a0);
+        a1 = fmaf(sdv[10 + l], bl, a1);
+        a2 = fmaf(sdv[20 + l], bl, a2);
+      }
+      acc[f][0] = a0; acc[f][1] = a1; acc[f][2] = a2;
+    }
+  }
+
+  for (int c = 0; c < kNChunks; ++c) {
+    const int s = c & 1;
+    if (c + 1 < kNChunks) {
+      if (tid == 0) {
+        mbar_expect_tx(&bars[s ^ 1], kChunkBytes);
+        tma_bulk_g2s(PDs + (s ^ 1) * kChunkFloats, pd_slab + (size_t)(c + 1) * kChunkFloats, kChunkBytes, &bars[s ^ 1]);
+      }
+      load_pf_chunk(c + 1, s ^ 1);
+    }
+    mbar_wait(&bars[s], (c >> 1) & 1);
+    const float* P = PDs + s * kChunkFloats + 3 * vl;
+    const float* F = pfs + s * kChunkK * kFramesPerCta + fg * kFramesPerThread;
+#pragma unroll
+    for (int k = 0; k < kChunkK; ++k) {
+      const float p0 = P[k * kTileCols + 0], p1 = P[k * kTileCols + 1], p2 = P[k * kTileCols + 2];
+#pragma unroll
+      for (int f4 = 0; f4 < kFramesPerThread / 4; ++f4) {
+        const float4 q = *reinterpret_cast<const float4*>(F + k * kFramesPerCta + f4 * 4);
+        acc[f4 * 4 + 0][0] = fmaf(q.x, p0, acc[f4 * 4 + 0][0]);
+        acc[f4 * 4 + 0][1] = fmaf(q.x, p1, acc[f4 * 4 + 0][1]);
+        acc[f4 * 4 + 0][2] = fmaf(q.x, p2, acc[f4 * 4 + 0][2]);
+        acc[f4 * 4 + 1][0] = fmaf(q.y, p0, acc[f4 * 4 + 1][0]);
+        acc[f4 * 4 + 1][1] = fmaf(q.y, p1, acc[f4 * 4 + 1][1]);
+        acc[f4 * 4 + 1][2] = fmaf(q.y, p2, acc[f4 * 4 + 1][2]);
+        acc[f4 * 4 + 2][0] = fmaf(q.z, p0, acc[f4 * 4 + 2][0]);
+        acc[f4 * 4 + 2][1] = fmaf(q.z, p1, acc[f4 * 4 + 2][1]);
+        acc[f4 * 4 + 2][2] = fmaf(q.z, p2, acc[f4 * 4 + 2][2]);
+        acc[f4 * 4 + 3][0] = fmaf(q.w, p0, acc[f4 * 4 + 3][0]);
+        acc[f4 * 4 + 3][1] = fmaf(q.w, p1, acc[f4 * 4 + 3][1]);
+        acc[f4 * 4 + 3][2] = fmaf(q.w, p2, acc[f4 * 4 + 3][2]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- skinning epilogue
+  int wj[KREG > 0 ? KREG : 1];
+  float ww[KREG > 0 ? KREG : 1];
+  if (KREG > 0) {
+#pragma unroll
+    for (int s = 0; s < KREG; ++s) {
+      wj[s] = m.skin_j[(size_t)gv * KREG + s];
+      ww[s] = m.skin_w[(size_t)gv * KREG + s];
+    }
+  }
+  const int ci = m.compact_of_vertex[gv];
+  const bool v_ok = gv < kV;
+#pragma unroll
+  for (int f = 0; f < kFramesPerThread; ++f) {
+    const int fl = fg * kFramesPerThread + f;
+    const int n = f0 + fl;
+    float T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = 0.0f;
+    if (KREG > 0) {
+#pragma unroll
+      for (int s = 0; s < KREG; ++s) {
+        const float4* a = reinterpret_cast<const float4*>(As + (fl * kNJ + wj[s]) * 12);
+        const float4 a0 = a[0], a1 = a[1], a2 = a[2];
+        const float wt = ww[s];
+        T[0] = fmaf(wt, a0.x, T[0]); T[1] = fmaf(wt, a0.y, T[1]); T[2] = fmaf(wt, a0.z, T[2]); T[3] = fmaf(wt, a0.w, T[3]);
+        T[4] = fmaf(wt, a1.x, T[4]); T[5] = fmaf(wt, a1.y, T[5]); T[6] = fmaf(wt, a1.z, T[6]); T[7] = fmaf(wt, a1.w, T[7]);
+        T[8] = fmaf(wt, a2.x, T[8]); T[9] = fmaf(wt, a2.y, T[9]); T[10] = fmaf(wt, a2.z, T[10]); T[11] = fmaf(wt, a2.w, T[11]);
+      }
+    } else {
+      for (int s = 0; s < m.K; ++s) {
+        const int jj = m.skin_j[(size_t)gv * m.K + s];
+        const float wt = m.skin_w[(size_t)gv * m.K + s];
+        const float* a = As + (fl * kNJ + jj) * 12;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = fmaf(wt, a[k], T[k]);
+      }
+    }
+    const float x = acc[f][0], y = acc[f][1], z = acc[f][2];
+    const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+    const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+    const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+    if (n < n_end && v_ok) {
+      if (vertices) {
+        float* o = vertices + ((size_t)n * kV + gv) * 3;
+        o[0] = ox; o[1] = oy; o[2] = oz;
+      }
+      if (ci >= 0) {
+        float* o = w.vcompact + ((size_t)n * m.S + ci) * 3;
+        o[0] = ox; o[1] = oy; o[2] = oz;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ joints_finalize
+// One warp per frame-person: gather the mapped joints from [24 LBS | picks | extra regressed], re-root at joint 0
+// and apply scale / root translation   (lib/models/smpl.py:299-315)
+__device__ __forceinline__ void raw_joint(const SmplDev& m, const SmplWorkspace& w, int f, int idx, float* o) {
+  if (idx < kNJ) {
+    const float* p = w.jposed + ((size_t)f * kNJ + idx) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  } else if (idx < kNJ + m.n_picks) {
+    const float* p = w.vcompact + ((size_t)f * m.S + m.pick_ci[idx - kNJ]) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  } else {
+    const int r = idx - kNJ - m.n_picks;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int e = m.reg_ptr[r]; e < m.reg_ptr[r + 1]; ++e) {
+      const float* p = w.vcompact + ((size_t)f * m.S + m.reg_ci[e]) * 3;
+      const float wt = m.reg_w[e];
+      a0 = fmaf(wt, p[0], a0); a1 = fmaf(wt, p[1], a1); a2 = fmaf(wt, p[2], a2);
+    }
+    o[0] = a0; o[1] = a1; o[2] = a2;
+  }
+}
+
+__global__ void __launch_bounds__(128) joints_finalize_kernel(SmplDev m, int n, int orig_joints, const float* __restrict__ root_trans,
+                                                              const float* __restrict__ root_scale, SmplWorkspace w,
+                                                              float* __restrict__ joints) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (f >= n) return;
+  const int n_out = orig_joints ? kNJ : m.n_map;
+  float root[3];
+  raw_joint(m, w, f, orig_joints ? 0 : m.joint_map[0], root);
+  if (lane == 0) {
+    w.root_raw[f * 3 + 0] = root[0]; w.root_raw[f * 3 + 1] = root[1]; w.root_raw[f * 3 + 2] = root[2];
+  }
+  const float sc = (root_trans && root_scale) ? root_scale[f] : 1.0f;
+  for (int k = lane; k < n_out; k += 32) {
+    float v[3];
+    raw_joint(m, w, f, orig_joints ? k : m.joint_map[k], v);
+    float* o = joints + ((size_t)f * n_out + k) * 3;
+    if (root_trans) {
+      o[0] = (v[0] - root[0]) * sc + root_trans[f * 3 + 0];
+      o[1] = (v[1] - root[1]) * sc + root_trans[f * 3 + 1];
+      o[2] = (v[2] - root[2]) * sc + root_trans[f * 3 + 2];
+    } else {
+      o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    }
+  }
+}
+
+__global__ void reroot_vertices_kernel(int n, const float* __restrict__ root_raw, const float* __restrict__ root_trans,
+                                       const float* __restrict__ root_scale, float* __restrict__ vertices) {
+  const size_t total = (size_t)n * kV * 3;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(e / (kV * 3));
+    const int c = (int)(e % 3);
+    const float sc = root_scale ? root_scale[f] : 1.0f;
+    vertices[e] = (vertices[e] - root_raw[f * 3 + c]) * sc + root_trans[f * 3 + c];
+  }
+}
+
+// fk-only joints (SMPL.get_joints): re-root the posed LBS joints
+__global__ void fk24_finalize_kernel(int n, const float* __restrict__ jposed, const float* __restrict__ root_trans,
+                                     const float* __restrict__ root_scale, float* __restrict__ joints) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * kNJ * 3) return;
+  const int f = e / (kNJ * 3), c = e % 3;
+  float v = jposed[e];
+  if (root_trans) {
+    const float sc = root_scale ? root_scale[f] : 1.0f;
+    v = (v - jposed[(size_t)f * kNJ * 3 + c]) * sc + root_trans[f * 3 + c];
+  }
+  joints[e] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* body_pose, const float* betas, int use_betas,
+                     const SmplWorkspace& w, cudaStream_t s) {
+  if (n <= 0) return GLAMR_OK;
+  const int blocks = (n + 3) / 4;
+  pose_prep_kernel<<<blocks, 128, 0, s>>>(m, n, orient, body_pose, betas, use_betas, w);
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+
+int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices, cudaStream_t s) {
+  if (n_end <= n_begin) return GLAMR_OK;
+  dim3 grid(kNVTiles, (n_end - n_begin + kFramesPerCta - 1) / kFramesPerCta);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbsSmemBytes));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbsSmemBytes));
+    attr_set = true;
+  }
+  if (m.K == 4)
+    lbs_kernel<4><<<grid, kLbsThreads, kLbsSmemBytes, s>>>(m, n_begin, n_end, betas, w, vertices);
+  else
+    lbs_kernel<0><<<grid, kLbsThreads, kLbsSmemBytes, s>>>(m, n_begin, n_end, betas, w, vertices);
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+
+int launch_joints_finalize(const SmplDev& m, int n, int orig_joints, const float* root_trans, const float* root_scale,
+                           const SmplWorkspace& w, float* joints, cudaStream_t s) {
+  if (n <= 0) return GLAMR_OK;
+  joints_finalize_kernel<<<(n + 3) / 4, 128, 0, s>>>(m, n, orig_joints, root_trans, root_scale, w, joints);
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+
+int launch_reroot_vertices(int n, const float* root_raw, const float* root_trans, const float* root_scale, float* vertices,
+                           cudaStream_t s) {
+  if (n <= 0) return GLAMR_OK;
+  const size_t total = (size_t)n * kV * 3;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  reroot_vertices_kernel<<<blocks, 256, 0, s>>>(n, root_raw, root_trans, root_scale, vertices);
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+
+}  // namespace glamr
+
+// =================================================================================================== C ABI
+using namespace glamr;
+
+namespace {
+template <typename T>
+int upload(glamr_smpl* h, const std::vector<T>& host, const T** dev) {
+  void* p = nullptr;
+  GLAMR_CUDA_TRY(cudaMalloc(&p, host.size() * sizeof(T) + 256));
+  GLAMR_CUDA_TRY(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  h->allocs[h->n_allocs++] = p;
+  *dev = (const T*)p;
+  return GLAMR_OK;
+}
+}  // namespace
+
+extern "C" int glamr_version(void) { return 100; }
+
+extern "C" int glamr_device_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return sms;
+}
+
+extern "C" int glamr_smpl_create(glamr_smpl_t** out, const float* v_template, const float* shapedirs, const float* posedirs,
+                                 const float* J_regressor, const float* lbs_weights, const int32_t* parents,
+                                 const float* J_regressor_extra, int n_extra, const int32_t* pick_vertex_ids, int n_picks,
+                                 const int32_t* joint_map, int n_map) {
+  if (!out || !v_template || !shapedirs || !posedirs || !J_regressor || !lbs_weights || !parents || !joint_map) return GLAMR_EINVAL;
+  if (n_extra < 0 || n_picks < 0 || n_map <= 0 || (n_extra > 0 && !J_regressor_extra) || (n_picks > 0 && !pick_vertex_ids)) return GLAMR_EINVAL;
+  for (int k = 0; k < n_map; ++k)
+    if (joint_map[k] < 0 || joint_map[k] >= kNJ + n_picks + n_extra) return GLAMR_EINVAL;
+  for (int k = 0; k < n_picks; ++k)
+    if (pick_vertex_ids[k] < 0 || pick_vertex_ids[k] >= kV) return GLAMR_EINVAL;
+  glamr_smpl* h = (glamr_smpl*)calloc(1, sizeof(glamr_smpl));
+  if (!h) return GLAMR_EINVAL;
+  SmplDev& d = h->dev;
+  // kinematic tree levels
+  for (int j = 0; j < kNJ; ++j) d.parents[j] = parents[j];
+  d.n_levels = 0;
+  for (int j = 0; j < kNJ; ++j) {
+    if (j > 0 && (parents[j] < 0 || parents[j] >= j)) { free(h); return GLAMR_EINVAL; }
+    d.level[j] = (j == 0) ? 0 : d.level[parents[j]] + 1;
+    if (d.level[j] + 1 > d.n_levels) d.n_levels = d.level[j] + 1;
+  }
+  d.n_extra = n_extra; d.n_picks = n_picks; d.n_map = n_map;
+  int rc = GLAMR_OK;
+  {  // posedirs -> [tile][k][384]
+    std::vector<float> t((size_t)kNVTiles * kPF * kTileCols, 0.0f);
+    for (int tile = 0; tile < kNVTiles; ++tile)
+      for (int k = 0; k < kPF; ++k) {
+        const int c0 = tile * kTileCols;
+        const int ncol = (c0 + kTileCols <= kV * 3) ? kTileCols : (kV * 3 - c0);
+        memcpy(&t[((size_t)tile * kPF + k) * kTileCols], posedirs + (size_t)k * kV * 3 + c0, ncol * sizeof(float));
+      }
+    if ((rc = upload(h, t, &d.pd_tiles))) goto fail;
+  }
+  {
+    std::vector<float> vt((size_t)kVPad * 3, 0.0f), sd((size_t)kVPad * 30, 0.0f);
+    memcpy(vt.data(), v_template, (size_t)kV * 3 * sizeof(float));
+    memcpy(sd.data(), shapedirs, (size_t)kV * 30 * sizeof(float));
+    if ((rc = upload(h, vt, &d.v_template))) goto fail;
+    if ((rc = upload(h, sd, &d.shapedirs))) goto fail;
+  }
+  {  // rest joints as an affine function of beta (double accumulation on the host)
+    std::vector<float> jt(kNJ * 3), js(kNJ * 3 * kNB);
+    for (int j = 0; j < kNJ; ++j)
+      for (int c = 0; c < 3; ++c) {
+        double a = 0.0;
+        double b[kNB] = {0};
+        for (int v = 0; v < kV; ++v) {
+          const double wv = J_regressor[(size_t)j * kV + v];
+          if (wv == 0.0) continue;
+          a += wv * v_template[v * 3 + c];
+          for (int l = 0; l < kNB; ++l) b[l] += wv * shapedirs[((size_t)v * 3 + c) * kNB + l];
+        }
+        jt[j * 3 + c] = (float)a;
+        for (int l = 0; l < kNB; ++l) js[(j * 3 + c) * kNB + l] = (float)b[l];
+      }
+    if ((rc = upload(h, jt, &d.j_template))) goto fail;
+    if ((rc = upload(h, js, &d.j_shapedirs))) goto fail;
+  }
+  {  // K-sparse skinning weights
+    int K = 1;
+    for (int v = 0; v < kV; ++v) {
+      int c = 0;
+      for (int j = 0; j < kNJ; ++j) c += lbs_weights[(size_t)v * kNJ + j] != 0.0f;
+      if (c > K) K = c;
+    }
+    if (K < 4) K = 4;
+    d.K = K;
+    std::vector<float> sw((size_t)kVPad * K, 0.0f);
+    std::vector<uint8_t> sj((size_t)kVPad * K, 0);
+    for (int v = 0; v < kV; ++v) {
+      int c = 0;
+      for (int j = 0; j < kNJ; ++j) {
+        const float wv = lbs_weights[(size_t)v * kNJ + j];
+        if (wv != 0.0f) { sw[(size_t)v * K + c] = wv; sj[(size_t)v * K + c] = (uint8_t)j; ++c; }
+      }
+    }
+    if ((rc = upload(h, sw, &d.skin_w))) goto fail;
+    if ((rc = upload(h, sj, &d.skin_j))) goto fail;
+  }
+  {  // support list + CSR of the extra regressor
+    std::vector<int32_t> cov(kVPad, -1), sup;
+    auto touch = [&](int v) { if (cov[v] < 0) { cov[v] = (int32_t)sup.size(); sup.push_back(v); } };
+    for (int k = 0; k < n_picks; ++k) touch(pick_vertex_ids[k]);
+    std::vector<int32_t> ptr(n_extra + 1, 0), ci;
+    std::vector<float> rw;
+    for (int r = 0; r < n_extra; ++r) {
+      for (int v = 0; v < kV; ++v) {
+        const float wv = J_regressor_extra[(size_t)r * kV + v];
+        if (wv != 0.0f) { touch(v); ci.push_back(cov[v]); rw.push_back(wv); }
+      }
+      ptr[r + 1] = (int32_t)ci.size();
+    }
+    if (ci.empty()) { ci.push_back(0); rw.push_back(0.0f); }
+    if (sup.empty()) touch(0);
+    d.S = (int)sup.size();
+    std::vector<int32_t> pci(n_picks > 0 ? n_picks : 1, 0), jm(joint_map, joint_map + n_map);
+    for (int k = 0; k < n_picks; ++k) pci[k] = cov[pick_vertex_ids[k]];
+    if ((rc = upload(h, cov, &d.compact_of_vertex))) goto fail;
+    if ((rc = upload(h, ptr, &d.reg_ptr))) goto fail;
+    if ((rc = upload(h, ci, &d.reg_ci))) goto fail;
+    if ((rc = upload(h, rw, &d.reg_w))) goto fail;
+    if ((rc = upload(h, pci, &d.pick_ci))) goto fail;
+    if ((rc = upload(h, jm, &d.joint_map))) goto fail;
+  }
+  *out = h;
+  return GLAMR_OK;
+fail:
+  glamr_smpl_destroy(h);
+  return rc;
+}
+
+extern "C" int glamr_smpl_destroy(glamr_smpl_t* m) {
+  if (!m) return GLAMR_OK;
+  for (int i = 0; i < m->n_allocs; ++i) cudaFree(m->allocs[i]);
+  free(m);
+  return GLAMR_OK;
+}
+
+extern "C" int glamr_smpl_info(const glamr_smpl_t* m, int what) {
+  if (!m) return GLAMR_EINVAL;
+  switch (what) {
+    case 0: return m->dev.K;
+    case 1: return m->dev.S;
+    case 2: return m->dev.n_map;
+    default: return GLAMR_EINVAL;
+  }
+}
+
+extern "C" size_t glamr_smpl_workspace_bytes(const glamr_smpl_t* m, int n) {
+  if (!m || n < 0) return 0;
+  return smpl_workspace_floats(n, m->dev.S) * sizeof(float);
+}
+
+extern "C" int glamr_smpl_forward(const glamr_smpl_t* m, int n, const float* global_orient, const float* body_pose,
+                                  const float* betas, const float* root_trans, const float* root_scale, int orig_joints,
+                                  float* joints, float* vertices, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || n < 0 || !body_pose || !betas || !joints || !workspace) return GLAMR_EINVAL;
+  if (workspace_bytes < glamr_smpl_workspace_bytes(m, n)) return GLAMR_ENOSPACE;
+  if (n == 0) return GLAMR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const SmplWorkspace w = smpl_carve_workspace(workspace, n, m->dev.S);
+  int rc;
+  if ((rc = launch_pose_prep(m->dev, n, global_orient, body_pose, betas, 1, w, s))) return rc;
+  if ((rc = launch_lbs(m->dev, 0, n, betas, w, vertices, s))) return rc;
+  if ((rc = launch_joints_finalize(m->dev, n, orig_joints, root_trans, root_scale, w, joints, s))) return rc;
+  if (vertices && root_trans)
+    if ((rc = launch_reroot_vertices(n, w.root_raw, root_trans, root_scale, vertices, s))) return rc;
+  return GLAMR_OK;
+}
+
+extern "C" int glamr_smpl_fk24(const glamr_smpl_t* m, int n, const float* global_orient, const float* body_pose,
+                               const float* root_trans, const float* root_scale, float* joints, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!m || n < 0 || !body_pose || !joints || !workspace) return GLAMR_EINVAL;
+  if (workspace_bytes < glamr_smpl_workspace_bytes(m, n)) return GLAMR_ENOSPACE;
+  if (n == 0) return GLAMR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const SmplWorkspace w = smpl_carve_workspace(workspace, n, m->dev.S);
+  int rc = launch_pose_prep(m->dev, n, global_orient, body_pose, nullptr, 0, w, s);
+  if (rc) return rc;
+  fk24_finalize_kernel<<<(n * kNJ * 3 + 255) / 256, 256, 0, s>>>(n, w.jposed, root_trans, root_scale, joints);
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}

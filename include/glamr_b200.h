@@ -1,0 +1,212 @@
+/* glamr_b200 -- C ABI of the B200 (sm_100a) CUDA library behind GLAMR's global-reconstruction path.
+ *
+ * GLAMR (NVlabs/GLAMR) is pure Python/PyTorch: it has no FFI layer, the seams a replacement binds to are Python
+ * call sites.  Each entry point below names the reference interface it stands behind (paths relative to the
+ * reference tree).  The Python host code in glamr_b200/ binds these with ctypes (INTEGRATION.md shows the stub a
+ * GLAMR maintainer would add).
+ *
+ * Conventions: plain C, no torch types.  Unless stated otherwise every pointer is a DEVICE pointer to contiguous
+ * row-major float32; `stream` is a cudaStream_t passed as void*.  Functions return 0 on success, a cudaError_t
+ * value (>0) for CUDA failures, or a negative GLAMR_E* code for argument errors.  They never synchronise the
+ * stream and never allocate device memory, except the *_create functions whose allocations are owned by the
+ * returned opaque handle and released by *_destroy.  All buffers are caller-owned.  Re-entrant across streams; no
+ * global state.
+ */
+#ifndef GLAMR_B200_H
+#define GLAMR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLAMR_OK 0
+#define GLAMR_EINVAL (-1)      /* bad argument / unsupported shape */
+#define GLAMR_ENOSPACE (-2)    /* workspace too small */
+#define GLAMR_EUNSUPPORTED (-3)
+
+#define GLAMR_NUM_VERTS 6890
+#define GLAMR_NUM_JOINTS 24
+#define GLAMR_NUM_BETAS 10
+#define GLAMR_NUM_POSE_FEAT 207
+
+int glamr_version(void);
+/* number of SMs / device ordinal the library sees for the current context (for grid sizing diagnostics) */
+int glamr_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SMPL body model  --  stands behind lib/models/smpl.py:274-343 (class SMPL: forward, get_joints) and the
+ * third-party smplx.lbs it calls (in-tree statement: HybrIK/hybrik/models/layers/smpl/lbs.py:195-288,402-548).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct glamr_smpl glamr_smpl_t;
+
+/* All constant arrays are HOST pointers (one-off upload; the library re-tiles them for its kernels).
+ *   v_template [6890,3]  shapedirs [6890,3,10]  posedirs [207,20670]  J_regressor [24,6890]
+ *   lbs_weights [6890,24]  parents [24]  J_regressor_extra [n_extra,6890]
+ *   pick_vertex_ids [n_picks]  (smplx VertexJointSelector)     joint_map [n_map] indexes [24 | n_picks | n_extra]
+ */
+int glamr_smpl_create(glamr_smpl_t** out, const float* v_template, const float* shapedirs, const float* posedirs,
+                      const float* J_regressor, const float* lbs_weights, const int32_t* parents,
+                      const float* J_regressor_extra, int n_extra, const int32_t* pick_vertex_ids, int n_picks,
+                      const int32_t* joint_map, int n_map);
+int glamr_smpl_destroy(glamr_smpl_t* m);
+/* introspection: 0 max skin weights per vertex, 1 support size (vertices feeding picks/regressors), 2 n_map */
+int glamr_smpl_info(const glamr_smpl_t* m, int what);
+size_t glamr_smpl_workspace_bytes(const glamr_smpl_t* m, int n);
+
+/* SMPL.forward (lib/models/smpl.py:289-316).  n frame-persons.
+ *   global_orient [n,3] (NULL -> zeros)  body_pose [n,69]  betas [n,10]
+ *   root_trans [n,3] or NULL (no re-rooting)   root_scale [n] or NULL (-> 1)
+ *   orig_joints != 0: joints = the 24 LBS joints, else the n_map mapped joints
+ *   joints [n, 24 or n_map, 3]   vertices [n,6890,3] or NULL
+ */
+int glamr_smpl_forward(const glamr_smpl_t* m, int n, const float* global_orient, const float* body_pose,
+                       const float* betas, const float* root_trans, const float* root_scale, int orig_joints,
+                       float* joints, float* vertices, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SMPL.get_joints (lib/models/smpl.py:318-343): FK only, rest joints from v_template (betas ignored). */
+int glamr_smpl_fk24(const glamr_smpl_t* m, int n, const float* global_orient, const float* body_pose,
+                    const float* root_trans, const float* root_scale, float* joints, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Row-wise rotation algebra  --  lib/utils/konia_transform.py:234-822, lib/utils/torch_transform.py:10-279.
+ * op codes: see glamr_b200/csrc/rowops.cuh (RowOp).  in1 may be NULL for unary ops; gin* may be NULL.
+ * ---------------------------------------------------------------------------------------------------------- */
+int glamr_rowop_fwd(int op, int n, const float* in0, const float* in1, float* out, void* stream);
+int glamr_rowop_vjp(int op, int n, const float* in0, const float* in1, const float* gout, float* gin0,
+                    float* gin1, void* stream);
+
+/* traj_pred/utils/traj_utils.py:65-88  traj_local2global_heading for B sequences of T frames, time-major
+ * local_traj [T,B,11] -> trans [T,B,3], orient_q [T,B,4] (local_orient_type '6d', local_heading on/off);
+ * scratch [B*T*3] floats */
+int glamr_traj_local2global(int T, int B, const float* local_traj, int local_heading, float* trans, float* orient_q,
+                            float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Global optimisation  --  stands behind GlobalReconOptimizer.forward / compute_loss / optimize_main
+ * (global_recon/models/global_recon_model.py:428-570), the residual registry global_recon/models/loss_func.py:314-340
+ * and torch.optim.Adam.step (:563,:642).
+ * ---------------------------------------------------------------------------------------------------------- */
+enum glamr_term {
+  GLAMR_T_KP_2D = 0, GLAMR_T_KP_2D_DIST, GLAMR_T_CAM_TRAJ_ROT, GLAMR_T_CAM_TRAJ_TRANS, GLAMR_T_TRAJ_ROT_SMOOTH,
+  GLAMR_T_TRAJ_TRANS_SMOOTH, GLAMR_T_REL_TRANSFORM, GLAMR_T_DXY_REG, GLAMR_T_DHEADING_REG, GLAMR_T_DHEADING_REG_NEW,
+  GLAMR_T_ROT_REG, GLAMR_T_Z_REG, GLAMR_T_ROT_RES, GLAMR_T_TRANS_RES, GLAMR_T_CAM_INV_TRANS_RES_REG,
+  GLAMR_T_CAM_INV_ROT_SMOOTH, GLAMR_T_CAM_ORIGIN_SMOOTH, GLAMR_T_CAM_UP_REG, GLAMR_T_CAM_ROT_SMOOTH,
+  GLAMR_T_CAM_TRANS_SMOOTH, GLAMR_NUM_TERMS
+};
+
+enum glamr_cam_mode {
+  GLAMR_CAM_CONST = 0,        /* camera is data (cam_pose_const)                           (:473 not taken)      */
+  GLAMR_CAM_PER_FRAME = 1,    /* variables cam_rot_6d [T,6], cam_trans [T,3]               (:478-480)            */
+  GLAMR_CAM_FIXED = 2,        /* variables cam_rot_6d_fix [1,6], cam_trans_fix [1,3]       (:475-477)            */
+  GLAMR_CAM_FROM_PERSONS = 3  /* mean of person_transform_world @ person2cam + residuals   (:481-508)            */
+};
+
+typedef struct glamr_person {
+  int32_t start, len;              /* exist range [start, start+len) of this person (exist_frames)              */
+  int32_t off_xy, off_heading, off_dxy, off_dheading, off_z, off_rot;     /* offsets into theta (floats)        */
+  int32_t off_world_dheading, off_orient_res, off_trans_res;              /* [T], [T,3], [T,3]                  */
+  int32_t pad_;
+  const float* traj_local_pred;    /* [len,11]                                                                    */
+  const float* orient_base_init;   /* [T,3] smpl_orient_world_base outside the exist range                        */
+  const float* trans_base_init;    /* [T,3]                                                                       */
+  const float* cam_K;              /* [T,9]                                                                       */
+  const float* kp_target;          /* [T,J,2] kp_2d_aligned                                                       */
+  const float* orient_cam_6d;      /* [T,6]  rot6d(R(smpl_orient_cam)), target of cam_traj_rot                    */
+  const float* trans_cam;          /* [T,3]  root_trans_cam                                                       */
+  const float* person2cam;         /* [T,12] 3x4, used by GLAMR_CAM_FROM_PERSONS                                  */
+  const float* dheading_mask;      /* [len-1] (cam_fix_frames)                                                    */
+  const float* rot_mask;           /* [len] or NULL (flag_opt_vis_local_rot)                                      */
+  const float* vis;                /* [T] 1/0 vis_frames                                                          */
+  /* per-stage weights, already containing score^2, min_conf, first-frame weighting, visibility               */
+  const float* kp_w;               /* [T,J]                                                                       */
+  const float* kp_dist_mask;       /* [T,J]                                                                       */
+  const float* ctr_w;              /* [T]  cam_traj_rot                                                           */
+  const float* ctt_w;              /* [T]  cam_traj_trans                                                         */
+} glamr_person_t;
+
+typedef struct glamr_problem {
+  int32_t P, T, J;                 /* persons, frames, joints per person (n_map of the SMPL handle)              */
+  int32_t cam_mode;                /* enum glamr_cam_mode                                                         */
+  int32_t off_cam_rot, off_cam_trans; /* variable offsets (modes 1,2: cam_rot_6d / cam_trans; mode 3: residuals)  */
+  int32_t use_world_res, has_world_dheading;
+  int32_t trans_res_all;           /* mode 3: cam_inv_trans_residual has T rows (else one row per empty frame)    */
+  int32_t cam_up_first_only;
+  int32_t n_params;                /* length of theta / grad / adam state                                         */
+  int32_t p_begin, p_end;          /* persons whose SMPL / per-frame residuals this rank evaluates (multi-GPU)   */
+  int32_t owner;                   /* != 0: this rank also evaluates the replicated terms (camera, regs, rel)    */
+  int32_t lbs_mode;                /* 0 full LBS every iteration, 1 rigid fast mode (cached body-frame joints)   */
+  int32_t pad_;
+  float cam_up_first_weight;
+  float rel_trans_weight;
+  float term_weight[GLAMR_NUM_TERMS];   /* YAML weight, 0 if the term is absent                                  */
+  float term_norm[GLAMR_NUM_TERMS];     /* normaliser (denominator) of the reference's mean                      */
+  int32_t term_enabled[GLAMR_NUM_TERMS];
+  int32_t term_monitor[GLAMR_NUM_TERMS];
+  const glamr_person_t* persons;   /* DEVICE array [P]                                                            */
+  const float* smpl_pose_all;      /* [P,T,69] body pose (infilled), constant during optimisation                 */
+  const float* smpl_beta_all;      /* [P,T,10]                                                                    */
+  const float* scale_all;          /* [P,T] or NULL                                                               */
+  const float* cam_pose_const;     /* [T,12] world->cam 3x4 (mode 0)                                              */
+  const int32_t* empty_index;      /* [T] row of cam_inv_rot_residual for frames without any person, else -1     */
+  const int32_t* fill_src;         /* [T] forward-fill source frame (mode 3)                                      */
+  const float* inv_num_persons;    /* [T] 1/num visible persons (0 where none)                                    */
+  const float* rel_target;         /* [P*P,T,12] rel_transform_cam (i*P+j), or NULL                               */
+  const float* rel_w;              /* [P*P,T] squared frame weights for the rotation part (0 = frame unused)      */
+  const float* rel_wt;             /* [P*P,T] same for the translation part                                       */
+  const uint8_t* active;           /* [n_params] 1 where Adam updates theta                                       */
+} glamr_problem_t;
+
+size_t glamr_sizeof_person(void);
+size_t glamr_sizeof_problem(void);
+
+typedef struct glamr_opt glamr_opt_t;
+
+/* The handle owns scratch sized for (P,T,J) and the Adam moments.  `problem` is copied (host struct; its embedded
+ * pointers are device pointers that must stay alive while the handle uses them). */
+int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, const glamr_problem_t* problem);
+int glamr_opt_destroy(glamr_opt_t* st);
+/* Re-read a modified problem description (new stage: weights, active mask, camera mode).  reset_adam != 0 zeroes the
+ * Adam moments and step count: the reference builds a fresh torch.optim.Adam per stage (global_recon_model.py:548,:642). */
+int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* problem, int reset_adam, void* stream);
+/* length (floats) of the caller-owned reduce buffer: [grad (n_params) | un-normalised term sums (GLAMR_NUM_TERMS)] */
+size_t glamr_opt_reduce_count(const glamr_opt_t* st);
+
+/* forward (trajectory, camera, SMPL, projection) + residuals + analytic backward for the current theta, leaving
+ * [grad | term sums] of THIS rank's share in reduce_buf.  With several GPUs the caller sums reduce_buf over ranks
+ * (one NCCL allreduce) before glamr_opt_apply.  (closure of global_recon_model.py:551-557) */
+int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream);
+/* loss_terms [GLAMR_NUM_TERMS+1] (device): un-weighted term values (sum / normaliser) then the weighted total.
+ * Then one torch.optim.Adam step (betas 0.9/0.999, eps 1e-8) on the active entries of theta; the step count and
+ * bias corrections live on the device so the call sequence can be captured in a CUDA graph.  With
+ * loss_hist_stride > 0 the terms of optimiser step k (0-based, counted on the device since the last reset) are
+ * written at loss_terms + k * loss_hist_stride, so a replayed graph fills a per-iteration history. */
+int glamr_opt_apply(glamr_opt_t* st, float* theta, const float* reduce_buf, double lr, float* loss_terms,
+                    int loss_hist_stride, void* stream);
+/* loss_terms only, no update (GlobalReconOptimizer.compute_loss, :533-545) */
+int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms, void* stream);
+
+enum glamr_read {
+  GLAMR_R_ORIENT_WORLD = 0,    /* [P,T,3]   smpl_orient_world            */
+  GLAMR_R_TRANS_WORLD = 1,     /* [P,T,3]   root_trans_world             */
+  GLAMR_R_ORIENT_BASE = 2,     /* [P,T,3]   smpl_orient_world_base       */
+  GLAMR_R_TRANS_BASE = 3,      /* [P,T,3]   root_trans_world_base        */
+  GLAMR_R_KP_PRED = 4,         /* [P,T,J,2] kp_2d_pred                   */
+  GLAMR_R_ORIENT_CAM_IN_WORLD = 5, /* [P,T,3]                            */
+  GLAMR_R_TRANS_CAM_IN_WORLD = 6,  /* [P,T,3]                            */
+  GLAMR_R_CAM_POSE = 7,        /* [T,12]    world->cam 3x4               */
+  GLAMR_R_CAM_POSE_INV = 8,    /* [T,12]                                 */
+  GLAMR_R_JOINTS_WORLD = 9,    /* [P,T,J,3]                              */
+  GLAMR_R_TRAJ_LOCAL = 10,     /* [P,T,11]  traj_local (rows of the exist range, others 0) */
+  GLAMR_R_SMPL_A = 11          /* [P,T,24,12] relative joint transforms of the last SMPL evaluation */
+};
+/* device pointer + element count of an internal output buffer (valid until the handle is destroyed) */
+int glamr_opt_read(glamr_opt_t* st, int what, const float** ptr, size_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLAMR_B200_H */

@@ -1,0 +1,111 @@
+"""The analytic backward + Adam of glamr_b200/csrc/globalopt_frames.cuh (host-compiled) against torch autograd of
+the oracle on the golden cases: iteration-0 gradients of every stage, residual values, and k-step trajectories."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from emu_runner import EmuRunner
+from glamr_b200 import lib as L
+from helpers import GLOBALOPT_CASES, ReplayMT, case_setup
+from oracle.global_opt import OracleGlobalRecon
+
+
+def _oracle_grads(model, data, specs, stage):
+    params = model.get_parameter(data, specs['opt_variables'])
+    for p in params:
+        p.requires_grad_(True)
+        p.grad = None
+    model.forward(data, specs['opt_variables'], {'stage': stage})
+    total, _, uw = model.compute_loss(data, specs['loss_cfg'])
+    total.backward()
+    grads = [None if p.grad is None else p.grad.detach().clone() for p in params]
+    for p in params:
+        p.requires_grad_(False)
+        p.grad = None
+    return params, grads, {k: float(v) for k, v in uw.items()}, float(total)
+
+
+def _param_views(runner, data, model, opt_variables):
+    """views of the emulator's grad/theta vectors in the order of get_parameter"""
+    lay = runner.layout
+    order = []
+    gv = lay.views(runner.reduce[:lay.n_params])
+    if 'cam' not in opt_variables:
+        order += [gv['cam_inv_rot_residual'], gv['cam_inv_trans_residual']]
+    elif model.flag_fixed_cam:
+        order += [gv['cam_rot_6d_fix'], gv['cam_trans_fix']]
+    else:
+        order += [gv['cam_rot_6d'], gv['cam_trans']]
+    for p in range(len(data['person_data'])):
+        pv = lay.views(runner.reduce[:lay.n_params], p)
+        for key in opt_variables:
+            if key == 'world_res':
+                order += [pv['smpl_orient_world_res'], pv['root_trans_world_res']]
+            if 'local' in key:
+                order.append(pv[f'traj_{key}'])
+        if 'world_dheading' in opt_variables:
+            order.append(pv['world_dheading'])
+    return order
+
+
+@pytest.mark.parametrize('name', GLOBALOPT_CASES)
+def test_gradients_and_steps_match_oracle(name, smpl_assets):
+    gold, cfg, in_dict = case_setup(name, smpl_assets)
+    ora = OracleGlobalRecon(cfg, smpl_assets, mt_model=ReplayMT(gold))
+    data_o = ora.init_data(copy.deepcopy(in_dict))
+    ora2 = OracleGlobalRecon(cfg, smpl_assets, mt_model=ReplayMT(gold))
+    data_e = ora2.init_data(copy.deepcopy(in_dict))           # identical starting state for the emulator
+    run = EmuRunner(ora2, data_e)
+    # init-stage forward (global_recon_model.py:246)
+    run.set_stage([], {}, 'init')
+    run.backward()
+    P, T = run.comp.P, run.comp.T
+    kp = run.buffer(L.R_KP_PRED).view(P, T, 26, 2)
+    for p, d in enumerate(data_o['person_data'].values()):
+        np.testing.assert_allclose(kp[p].numpy(), d['kp_2d_pred'].numpy(), atol=2e-3, err_msg='init kp_2d_pred')
+    for stage, specs in cfg.opt_stage_specs.items():
+        params, grads, uw, total = _oracle_grads(ora, data_o, specs, stage)
+        run.set_stage(specs['opt_variables'], specs['loss_cfg'], stage)
+        g_all, terms = run.backward()
+        for k, v in uw.items():
+            got = float(terms[L.TERM_INDEX[k]])
+            assert abs(got - v) <= 2e-4 * max(abs(v), 1e-3) + 1e-7, f'{stage} term {k}: {got} vs {v}'
+        assert abs(float(terms[-1]) - total) <= 2e-4 * abs(total) + 1e-6
+        views = _param_views(run, data_e, ora2, specs['opt_variables'])
+        assert len(views) == len(params)
+        for i, (gv, gr) in enumerate(zip(views, grads)):
+            if gr is None:
+                assert float(gv.abs().max()) == 0.0 if gv.numel() else True
+                continue
+            scale = max(float(gr.abs().max()), 1e-9)
+            err = float((gv.reshape(gr.shape) - gr).abs().max()) / scale
+            assert err < 3e-4, f'{stage} grad of param {i} shape {tuple(gr.shape)}: rel err {err:.2e} (scale {scale:.2e})'
+        # k optimiser steps in both.  Adam moves every element by ~lr*sign(g) per step, so an element whose true
+        # gradient is zero (e.g. the scale directions of a 6d rotation on frames without observations) random-walks
+        # on rounding noise in BOTH implementations; compare elements with a meaningful gradient, and the loss.
+        n = specs['opt_niters']
+        loss_o, loss_e = [], []
+        ora.optimize_main(data_o, specs['opt_variables'], specs['opt_lr'], n, specs['loss_cfg'], {'stage': stage},
+                          on_iter=lambda it, last, dt: loss_o.append(float(last['loss'])))
+        for it in range(n):
+            _, terms = run.backward()
+            loss_e.append(float(terms[-1]))
+            run.step(specs['opt_lr'])
+        np.testing.assert_allclose(loss_e, loss_o, rtol=2e-3, err_msg=f'{stage} loss trajectory')
+        lay = run.layout
+        grad_of = {id(p_): g_ for p_, g_ in zip(params, grads)}
+        for p, d in enumerate(data_o['person_data'].values()):
+            pv = lay.views(run.theta, p)
+            for key in ['traj_local_xy', 'traj_local_heading', 'traj_local_rot', 'traj_local_dxy', 'traj_local_z', 'world_dheading']:
+                if key in d and id(d[key]) in grad_of and grad_of[id(d[key])] is not None:
+                    g0 = grad_of[id(d[key])].reshape(pv[key].shape).abs()
+                    sel = g0 > 1e-3 * g0.max()
+                    diff = (pv[key] - d[key].detach().reshape(pv[key].shape)).abs()
+                    tol = 2e-2 * specs['opt_lr'] * n + 1e-6
+                    assert float(diff[sel].max()) < tol, f'{stage} after {n} steps: {key} differs by {float(diff[sel].max()):.2e}'
+        # hand the emulator's camera to its data dict like optimize_main does (:568-569)
+        cam = run.buffer(L.R_CAM_POSE).view(T, 3, 4)
+        np.testing.assert_allclose(cam.numpy(), data_o['cam_pose'][:, :3, :].numpy(), atol=2e-4, err_msg=f'{stage} cam_pose')
+        data_e['cam_pose'] = torch.cat([cam, torch.tensor([0., 0., 0., 1.]).expand(T, 1, 4)], dim=1).clone()
