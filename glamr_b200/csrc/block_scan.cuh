@@ -7,7 +7,7 @@ namespace glamr {
 constexpr int kScanThreads = 256;
 
 // Inclusive scan (forward or reverse) of `count` floats at data[k * stride], in place, by one CTA of kScanThreads.
-__device__ void block_scan_inplace(float* data, int count, int stride, bool reverse, float* smem /*[kScanThreads/32 + 1]*/) {
+__device__ __forceinline__ void block_scan_inplace(float* data, int count, int stride, bool reverse, float* smem /*[kScanThreads/32 + 1]*/) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NW = kScanThreads / 32;
   float carry = 0.0f;

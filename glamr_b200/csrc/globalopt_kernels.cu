@@ -206,6 +206,8 @@ struct glamr_opt {
   void* arena;
   size_t arena_bytes;
   float gs[GLAMR_NUM_TERMS];
+  int timing;                 // != 0: bracket the LBS kernel with events (bench / roofline only, not graph-capturable)
+  cudaEvent_t ev_lbs0, ev_lbs1;
 };
 
 extern "C" size_t glamr_sizeof_person(void) { return sizeof(glamr_person_t); }
@@ -273,8 +275,26 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   return GLAMR_OK;
 }
 
+extern "C" int glamr_opt_kernel_timing(glamr_opt_t* st, int enable) {
+  if (!st) return GLAMR_EINVAL;
+  if (enable && !st->ev_lbs0) {
+    GLAMR_CUDA_TRY(cudaEventCreate(&st->ev_lbs0));
+    GLAMR_CUDA_TRY(cudaEventCreate(&st->ev_lbs1));
+  }
+  st->timing = enable;
+  return GLAMR_OK;
+}
+
+extern "C" int glamr_opt_last_lbs_ms(glamr_opt_t* st, float* ms) {
+  if (!st || !ms || !st->ev_lbs0) return GLAMR_EINVAL;
+  GLAMR_CUDA_TRY(cudaEventSynchronize(st->ev_lbs1));
+  GLAMR_CUDA_TRY(cudaEventElapsedTime(ms, st->ev_lbs0, st->ev_lbs1));
+  return GLAMR_OK;
+}
+
 extern "C" int glamr_opt_destroy(glamr_opt_t* st) {
   if (!st) return GLAMR_OK;
+  if (st->ev_lbs0) { cudaEventDestroy(st->ev_lbs0); cudaEventDestroy(st->ev_lbs1); }
   cudaFree(st->arena);
   free(st);
   return GLAMR_OK;
@@ -320,7 +340,9 @@ extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* re
     int rc;
     if ((rc = launch_pose_prep(st->smpl, nn, st->sc.orient_world + (size_t)n_begin * 3, pb.smpl_pose_all + (size_t)n_begin * 69,
                                pb.smpl_beta_all + (size_t)n_begin * kNB, 1, wo, s))) return rc;
+    if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
     if ((rc = launch_lbs(st->smpl, 0, nn, pb.smpl_beta_all + (size_t)n_begin * kNB, wo, nullptr, s))) return rc;
+    if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
     if ((rc = launch_joints_finalize(st->smpl, nn, 0, st->sc.trans_world + (size_t)n_begin * 3,
                                      pb.scale_all ? pb.scale_all + n_begin : nullptr, wo,
                                      st->sc.joints_world + (size_t)n_begin * pb.J * 3, s))) return rc;

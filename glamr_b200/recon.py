@@ -1,0 +1,553 @@
+"""``GlobalReconOptimizer`` -- drop-in for the reference class of the same name
+(global_recon/models/global_recon_model.py:23-659) with the optimisation loop running in the CUDA library.
+
+Same constructor, ``optimize(in_dict, continue_opt=False) -> dict`` (numpy), ``init_data``, ``forward``,
+``compute_loss``, ``optimize_main``; same YAML stage specs; same output keys / shapes / dtypes.
+Host Python does what the reference does on the host (dict bookkeeping, SciPy rotation-vector conversion and linear
+gap interpolation, log lines); every formula of the per-iteration path -- trajectory codec, camera, SMPL, projection,
+residuals, analytic backward, Adam -- is a kernel of glamr_b200/csrc.  No autograd, no CPU fallback.
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+from scipy.interpolate import interp1d
+from scipy.spatial.transform import Rotation
+
+from . import geometry as G
+from . import lib as L
+from . import problem as PB
+from .smpl import SMPL, SMPL_MODEL_DIR
+from .synthetic import SMPL_TO_BODY26FK
+
+NUM_TERMS = L.NUM_TERMS
+_TERM_NAMES = {v: k for k, v in L.TERM_INDEX.items()}
+
+
+def tensor_to(x, device):
+    """lib/utils/torch_utils.py:101 -- numpy / nested containers -> tensors on `device` (dtype preserved)"""
+    if isinstance(x, np.ndarray):
+        return torch.tensor(x, device=device)
+    if isinstance(x, (np.floating, np.integer, np.bool_)):
+        return torch.tensor(x, device=device)
+    if isinstance(x, torch.Tensor):
+        return x.to(device)
+    if isinstance(x, dict):
+        return {k: tensor_to(v, device) for k, v in x.items()}
+    return x
+
+
+def tensor_to_numpy(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    if isinstance(x, dict):
+        return {k: tensor_to_numpy(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return type(x)(tensor_to_numpy(v) for v in x)
+    return x
+
+
+def _sec_to_time(secs):
+    secs = int(secs)
+    return f'{secs // 3600}:{(secs % 3600) // 60:02d}:{secs % 60:02d}'
+
+
+class GlobalReconOptimizer:
+
+    def __init__(self, cfg, device=torch.device('cuda'), log=None, smpl=None, mt_model=None, dist=None):
+        """cfg/device/log as in the reference (:25).  Extra, optional:
+        smpl      a glamr_b200.smpl.SMPL (or an assets dict); default loads SMPL_MODEL_DIR like the reference
+        mt_model  object with .inference(batch, sample_num) (the learned prior); default: the CUDA MotionTrajJointModel
+        dist      (rank, world_size) for person sharding across GPUs (torch.distributed must be initialised)"""
+        self.cfg = cfg
+        self.specs = specs = cfg.grecon_model_specs
+        self.device = L.require_cuda(device)
+        self.log = log
+        self.cur_iter = 0
+        if isinstance(smpl, SMPL):
+            self.smpl = smpl
+        else:
+            self.smpl = SMPL(smpl if smpl is not None else SMPL_MODEL_DIR, pose_type='body26fk', device=self.device)
+        g = specs.get
+        self.use_gt = g('use_gt', False)
+        self.est_type = g('est_type', 'hybrik')
+        self.flag_infer_motion_traj = g('flag_infer_motion_traj', False)
+        self.flag_infill_motion = g('flag_infill_motion', True)
+        self.flag_pred_traj = g('flag_pred_traj', True)
+        self.flag_opt_traj = g('flag_opt_traj', True)
+        self.flag_opt_cam = g('flag_opt_cam', True)
+        self.flag_fixed_cam = g('flag_fixed_cam', False)
+        self.flag_opt_vis_local_rot = g('flag_opt_vis_local_rot', False)
+        self.flag_cam_inv_trans_res_all = g('flag_cam_inv_trans_res_all', True)
+        self.flag_filter_pose = g('flag_filter_pose', True)
+        self.flag_make_invis_with_keypoint = g('flag_make_invis_with_keypoint', False)
+        self.make_invis_keypoint_min_score = g('make_invis_keypoint_min_score', 0.6)
+        self.make_invis_keypoint_min_num = g('make_invis_keypoint_min_num', 15)
+        self.flag_opt_cam_from_person_pose = g('flag_opt_cam_from_person_pose', False)
+        self.flag_init_cam_all_frames = g('flag_init_cam_all_frames', False)
+        self.cam_fix_frames = g('cam_fix_frames', [[0, None]])
+        self.opt_stage_specs = self.cfg.opt_stage_specs
+        for flag in ['flag_opt_motion_latent', 'flag_opt_traj_latent', 'flag_use_pen_loss', 'flag_traj_from_cam', 'absolute_heading',
+                     'flag_opt_person2cam_rot', 'flag_opt_person2cam_trans']:
+            if g(flag, False):
+                raise NotImplementedError(f'{flag} is not implemented in the CUDA path (SURVEY.md §8(f)-4); no CPU fallback')
+        if g('heading_type', 'scalar') != 'scalar':
+            raise NotImplementedError("heading_type 'vec' is not implemented in the CUDA path")
+        if not self.flag_opt_traj:
+            raise NotImplementedError('flag_opt_traj=false is not implemented in the CUDA path')
+        self.rank, self.world = dist if dist is not None else (0, 1)
+        self.lbs_mode = g('lbs_mode', 'full')
+        self.log_interval = g('log_interval', 1)
+        self.use_cuda_graph = g('use_cuda_graph', True)
+        self.mt_cfg = None
+        self.mt_model = mt_model
+        if mt_model is None and 'motion_traj_cfg' in specs and self.flag_infer_motion_traj:
+            self.load_model()
+        self._lib = L.load()
+        self._opt = None
+        self.iter_ms = []              # (stage, niters, ms per iteration) of every optimize_main call
+
+    def load_model(self):
+        from .motion_traj import MotionTrajJointModel
+        self.mt_model = MotionTrajJointModel(self.specs['motion_traj_cfg'], self.device, self.log, smpl=self.smpl)
+        self.mt_cfg = getattr(self.mt_model, 'cfg', None)
+
+    @property
+    def _flags(self):
+        return {k: getattr(self, k) for k in ['flag_fixed_cam', 'flag_opt_cam', 'flag_opt_cam_from_person_pose',
+                                              'flag_cam_inv_trans_res_all', 'flag_opt_vis_local_rot', 'cam_fix_frames']}
+
+    # ------------------------------------------------------------------------------------------------ init_data
+    def _person_from_estimate(self, est, gt_entry):
+        """global_recon_model.py:88-137 (host side, numpy/SciPy exactly as the reference)"""
+        d = {}
+        visible = est['bboxes_dict']['exist'].copy()
+        d['visible'] = visible
+        d['visible_orig'] = visible.copy()
+        where = np.where(visible)[0]
+        start, end = where[0], where[-1] + 1
+        d['fr_start'], d['fr_end'] = start, end
+        exist = visible == 1
+        exist[start:end] = True
+        d['exist_frames'] = exist
+        d['exist_len'] = end - start
+        d['max_len'] = n = visible.shape[0]
+        d['frames'] = np.arange(n)
+        d['vis_frames'] = vis = visible == 1
+        d['invis_frames'] = visible == 0
+        d['frame2ind'] = {f: i for i, f in enumerate(d['frames'])}
+        d['scale'] = None
+        rotmats = est['smpl_pose_quat_wroot']
+        nv = rotmats.shape[0]
+        aa = Rotation.from_matrix(rotmats.reshape(-1, 3, 3)).as_rotvec().reshape(nv, -1, 3).astype(np.float32)
+        d['smpl_pose'] = aa[:, 1:].reshape(-1, 69)
+        if gt_entry is not None:
+            d['smpl_pose_gt'] = gt_entry['pose'][:, 3:]
+        d['smpl_beta'] = est['smpl_beta']
+        d['smpl_orient_cam'] = aa[:, 0]
+        d['root_trans_cam'] = est['root_trans']
+        j2d = est['kp_2d'][:, :24]
+        j2d = np.concatenate([j2d, np.ones_like(j2d[:, :, :1])], axis=-1)
+        kp = np.zeros((int(vis.sum()), 26, 3))
+        kp[:, SMPL_TO_BODY26FK[:, 0]] = j2d[:, SMPL_TO_BODY26FK[:, 1]]
+        d['kp_2d'], d['kp_2d_score'] = kp[:, :, :2], kp[:, :, 2]
+        d['kp_2d_aligned'] = d['kp_2d'].copy()
+        d['cam_K'] = est['cam_K'].astype(np.float32)
+        if not np.all(visible):
+            for key in ['kp_2d', 'kp_2d_score', 'kp_2d_aligned', 'cam_K']:
+                full = np.zeros((n,) + d[key].shape[1:], dtype=d[key].dtype)
+                full[vis] = d[key]
+                d[key] = full
+            vis_ind = np.where(visible)[0].astype(np.float32)
+            for key in ['smpl_pose', 'smpl_beta', 'root_trans_cam', 'smpl_orient_cam']:
+                f = interp1d(vis_ind, d[key], axis=0, assume_sorted=True, fill_value='extrapolate')
+                d[key] = f(np.arange(n, dtype=np.float32))
+        return tensor_to(d, self.device)
+
+    def filter_pose(self, d):
+        """:250-271"""
+        visible = d['visible']
+        q = G.angle_axis_to_quaternion(d['smpl_orient_cam'].float())
+        jump = G.quat_angle_diff(q[1:], q[:-1])
+        ind = (torch.where((jump > np.pi / 3) & visible[1:].bool())[0] + 1).tolist()
+        for i in ind:
+            if visible[i - 1]:
+                if i + 1 < q.shape[0] and visible[i + 1] and (i + 1) not in ind:
+                    visible[i - 1] = 0
+                else:
+                    visible[i] = 0
+        if self.flag_make_invis_with_keypoint:
+            vis_ind = torch.where(visible == 1.0)[0]
+            nvalid = (d['kp_2d_score'][vis_ind] > self.make_invis_keypoint_min_score).sum(dim=1)
+            visible[vis_ind[nvalid < self.make_invis_keypoint_min_num]] = 0.0
+        d['vis_frames'] = visible == 1
+        d['invis_frames'] = visible == 0
+
+    def infer_motion_traj(self, d):
+        """:353-392"""
+        if self.mt_model is None:
+            return
+        ex = d['exist_frames']
+        batch = {'in_body_pose': d['smpl_pose_nofill'][ex].unsqueeze(0).clone(), 'frame_mask': d['visible'][ex].unsqueeze(0).clone()}
+        out = self.mt_model.inference(batch, sample_num=1)
+        if self.flag_infill_motion:
+            d['infilled'] = True
+            d['smpl_pose'] = d['smpl_pose'].detach().clone()
+            d['smpl_pose'][ex] = out['infer_out_body_pose'][0, 0].to(d['smpl_pose'])
+        if self.flag_pred_traj:
+            d['traj_predicted'] = True
+            d['traj_local_pred'] = out['infer_out_local_traj_tp'][:, 0, 0, :].clone().float()
+            d['smpl_orient_world_base'] = d['smpl_orient_world_base'].detach().clone()
+            d['root_trans_world_base'] = d['root_trans_world_base'].detach().clone()
+            if 'infer_out_pose' in out:
+                d['smpl_orient_world_base'][ex] = out['infer_out_pose'][0, 0, :, :3].to(d['smpl_orient_world_base'])
+            if 'infer_out_orient' in out:
+                d['smpl_orient_world_base'][ex] = out['infer_out_orient'][0, 0].to(d['smpl_orient_world_base'])
+            d['root_trans_world_base'][ex] = out['infer_out_trans'][0, 0].to(d['root_trans_world_base'])
+            d['smpl_orient_world'] = d['smpl_orient_world_base']
+            d['root_trans_world'] = d['root_trans_world_base']
+
+    def init_default_traj(self, d):
+        """:319-323"""
+        d['root_trans_world_base'][:] = torch.tensor([0.0, 0.0, 0.8], device=self.device)
+        d['smpl_orient_world_base'][:] = G.quaternion_to_angle_axis(torch.tensor([[0.0, 0.0, 0.7071, 0.7071]], device=self.device))[0]
+        d['root_trans_world'] = d['root_trans_world_base']
+        d['smpl_orient_world'] = d['smpl_orient_world_base']
+
+    def init_cam_pose(self, data, all_frames=False):
+        """:294-317"""
+        cands = [torch.matmul(d['person_transform_world'], d['person2cam']) * d['vis_frames'][:, None, None]
+                 for d in data['person_data'].values()]
+        npers = data['fr_num_persons']
+        has = npers > 0
+        start = torch.where(has)[0][0]
+        inv = torch.zeros_like(data['cam_pose'])
+        inv[has] = cands[0][has]
+        data['pose_infer_cam_pose_inv'] = inv
+        if all_frames:
+            if not torch.all(has):
+                last = inv[start]
+                for i in range(len(npers)):
+                    if npers[i] == 0:
+                        data['cam_pose_inv'][i] = last
+                    else:
+                        last = data['cam_pose_inv'][i]
+        else:
+            inv[...] = inv[start].clone()
+        inv[:, :3, :3] = G.rot6d_to_rotmat(G.rotmat_to_rot6d(inv[:, :3, :3]))
+        data['cam_pose_inv'] = inv
+        data['cam_pose'] = G.inverse_transform(inv)
+
+    def _traj_local2global(self, local, local_heading=True):
+        """traj_pred/utils/traj_utils.py:65-88 for one sequence [T,11] -> trans [T,3], orient_q [T,4]"""
+        T = local.shape[0]
+        loc = local.reshape(T, 1, 11).contiguous().float()
+        trans = torch.empty((T, 1, 3), device=self.device)
+        oq = torch.empty((T, 1, 4), device=self.device)
+        scratch = torch.empty(T * 3, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.glamr_traj_local2global(T, 1, L.ptr(loc), int(local_heading), L.ptr(trans), L.ptr(oq), L.ptr(scratch),
+                                                      L.stream_ptr()), 'glamr_traj_local2global')
+        return trans[:, 0], oq[:, 0]
+
+    def _traj_global2local(self, trans, orient_q):
+        """traj_pred/utils/traj_utils.py:44-62 (init only)"""
+        base = torch.tensor([0.5, 0.5, 0.5, 0.5], device=self.device)
+        xy, z = trans[..., :2], trans[..., 2]
+        q = G.quat_mul(orient_q, G.quat_conjugate(base).expand_as(orient_q))
+        heading = G.get_heading(q)
+        d6 = G.quat_to_rot6d(G.deheading_quat(q, G.get_heading_q(q)))
+        d_heading = torch.cat([heading[:1], heading[1:] - heading[:-1]])
+        hvec = G.heading_to_vec(d_heading)
+        dxy = xy[1:] - xy[:-1]
+        th = -heading[:-1]
+        c, s = torch.cos(th), torch.sin(th)
+        dxy_h = torch.stack([dxy[:, 0] * c - dxy[:, 1] * s, dxy[:, 0] * s + dxy[:, 1] * c], dim=-1)
+        return torch.cat([torch.cat([xy[:1], dxy_h]), z.unsqueeze(-1), d6, hvec], dim=-1)
+
+    def _interp_orient_q_sep_heading(self, orient_q_vis, vis_frames):
+        """traj_pred/utils/traj_utils.py:120-142 (SciPy linear interpolation on the host, as the reference)"""
+        base = torch.tensor([0.5, 0.5, 0.5, 0.5], device=self.device)
+        q = G.quat_mul(orient_q_vis, G.quat_conjugate(base).expand_as(orient_q_vis))
+        hq = G.get_heading_q(q)
+        hvec = G.heading_to_vec(G.get_heading(q))
+        d6 = G.quat_to_rot6d(G.deheading_quat(q, hq))
+        n = vis_frames.shape[0]
+        vis_ind = torch.where(vis_frames)[0].cpu().numpy()
+        grid = np.arange(n, dtype=np.float32)
+        f = interp1d(vis_ind, hvec.cpu().numpy(), axis=0, assume_sorted=True, fill_value='extrapolate')
+        hvec_i = torch.tensor(f(grid), device=self.device, dtype=torch.float32)
+        f = interp1d(vis_ind, d6.cpu().numpy(), axis=0, assume_sorted=True, fill_value='extrapolate')
+        d6_i = torch.tensor(f(grid), device=self.device, dtype=torch.float32)
+        out = G.quat_mul(G.heading_to_quat(G.vec_to_heading(hvec_i)), G.rot6d_to_quat(d6_i))
+        return G.quat_mul(out, base.expand_as(out))
+
+    def init_traj_heading_from_cam(self, data):
+        """:273-292"""
+        for d in data['person_data'].values():
+            world = torch.matmul(data['cam_pose_inv'], d['person_transform_cam'])
+            q = G.rotation_matrix_to_quaternion(world[:, :3, :3].contiguous())
+            q_interp = self._interp_orient_q_sep_heading(q[d['vis_frames']], d['vis_frames'])
+            local = self._traj_global2local(world[:, :3, 3], q_interp)
+            for (s, e) in self.cam_fix_frames:
+                d['traj_local_pred'][s:e, -2:] = local[d['exist_frames']][s:e, -2:]
+            trans, oq = self._traj_local2global(d['traj_local_pred'])
+            ex = d['exist_frames']
+            d['smpl_orient_world_base'] = d['smpl_orient_world_base'].detach().clone()
+            d['root_trans_world_base'] = d['root_trans_world_base'].detach().clone()
+            d['smpl_orient_world_base'][ex] = G.quaternion_to_angle_axis(oq)
+            d['root_trans_world_base'][ex] = trans
+            d['smpl_orient_world'] = d['smpl_orient_world_base'].clone()
+            d['root_trans_world'] = d['root_trans_world_base'].clone()
+            d['person_transform_world'] = G.make_transform(d['smpl_orient_world'], d['root_trans_world'], 'axis_angle')
+
+    def init_data(self, in_dict):
+        if self.est_type != 'hybrik':
+            raise ValueError(f'est_type {self.est_type} not supported')
+        dev = self.device
+        num_fr = len(in_dict['est'][0]['bboxes_dict']['exist'])
+        cam_pose = torch.eye(4, device=dev).repeat(num_fr, 1, 1)
+        cam_pose_inv = G.inverse_transform(cam_pose)
+        persons = {}
+        for idx, est in in_dict['est'].items():
+            d = self._person_from_estimate(est, in_dict['gt'].get(idx))
+            if self.flag_filter_pose:
+                self.filter_pose(d)
+            d['root_trans_world'] = G.transform_trans(cam_pose_inv, d['root_trans_cam'].float())
+            d['smpl_orient_world'] = G.transform_rot(cam_pose_inv, d['smpl_orient_cam'].float())
+            d['root_trans_world_base'] = d['root_trans_world'].clone()
+            d['smpl_orient_world_base'] = d['smpl_orient_world'].clone()
+            d['smpl_pose_nofill'] = d['smpl_pose'].clone()
+            d['smpl_pose_nofill'][~d['exist_frames']] = 0.0
+            persons[idx] = d
+        if self.flag_infer_motion_traj:
+            for d in persons.values():
+                self.infer_motion_traj(d)
+        if not (self.flag_infer_motion_traj and self.flag_pred_traj):
+            raise NotImplementedError('flag_pred_traj=false (default trajectory) is not implemented in the CUDA path')
+        for d in persons.values():
+            d['person_transform_world'] = G.make_transform(d['smpl_orient_world'], d['root_trans_world'], 'axis_angle')
+            d['person_transform_cam'] = G.make_transform(d['smpl_orient_cam'].float(), d['root_trans_cam'].float(), 'axis_angle')
+            d['person2cam'] = G.inverse_transform(d['person_transform_cam'])
+        last = d
+        for d in persons.values():
+            d['smpl_orient_world_res'] = torch.zeros_like(last['smpl_orient_world'])
+            d['root_trans_world_res'] = torch.zeros_like(last['root_trans_world'])
+        rel = {}
+        ids = list(persons.keys())
+        for i in range(len(ids)):
+            for j in range(len(ids)):
+                if i != j:
+                    rel[(i, j)] = torch.matmul(G.inverse_transform(persons[ids[i]]['person_transform_cam']), persons[ids[j]]['person_transform_cam'])
+        for d in persons.values():
+            Ln = int(d['exist_len'].sum())
+            d['traj_local_xy'] = torch.zeros(2, device=dev)
+            d['traj_local_dxy'] = torch.zeros(Ln - 1, 2, device=dev)
+            d['traj_local_heading'] = torch.zeros(1, device=dev)
+            d['traj_local_dheading'] = torch.zeros(Ln - 1, device=dev)
+            d['traj_local_z'] = torch.zeros(Ln, device=dev)
+            d['traj_local_rot'] = torch.zeros(Ln, 6, device=dev)
+        fr_num_persons = sum(d['vis_frames'] for d in persons.values())
+        n_empty = int((fr_num_persons == 0).sum())
+        data = {
+            'seq_name': in_dict['seq_name'], 'person_data': persons, 'seq_len': num_fr, 'fr_num_persons': fr_num_persons,
+            'cam_pose': cam_pose, 'cam_pose_inv': cam_pose_inv,
+            'cam_inv_rot_residual': torch.zeros(n_empty, 6, device=dev),
+            'cam_inv_trans_residual': torch.zeros(num_fr if self.flag_cam_inv_trans_res_all else n_empty, 3, device=dev),
+            'rel_transform_cam': rel, 'gt': in_dict['gt'], 'gt_meta': in_dict['gt_meta'],
+            'meta': {'algo': 'global_recon', 'mt_cfg': getattr(self.mt_cfg, 'yml_dict', None), 'num_fr': num_fr},
+        }
+        self.init_cam_pose(data)
+        self.init_traj_heading_from_cam(data)
+        if self.flag_init_cam_all_frames:
+            self.init_cam_pose(data, all_frames=True)
+        self._attach(data)
+        self.forward(data, [], {'stage': 'init'})
+        return data
+
+    # ------------------------------------------------------------------------------------------------ device state
+    def _attach(self, data):
+        """Pack the optimisation variables into theta, build the constant tables and create the CUDA handle."""
+        self._release()
+        self._data = data
+        self._layout = PB.make_layout(data, self._flags)
+        self._theta = torch.zeros(self._layout.n_params, device=self.device)
+        PB.bind_variables(data, self._layout, self._theta)
+        self._comp = PB.StageCompiler(data, self._layout, self._flags, self.device, G.angle_axis_to_rot6d, num_joints=self.smpl.num_joints)
+        self._reduce = torch.zeros(self._layout.n_params + NUM_TERMS, device=self.device)
+        self._terms = torch.zeros(NUM_TERMS + 1, device=self.device)
+        self._stage_key = None
+        P = self._comp.P
+        if self.world > 1:
+            per = (P + self.world - 1) // self.world
+            self._p_range = (min(self.rank * per, P), min((self.rank + 1) * per, P))
+        else:
+            self._p_range = (0, P)
+
+    def _release(self):
+        if getattr(self, '_opt', None):
+            self._lib.glamr_opt_destroy(self._opt)
+        self._opt = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _set_stage(self, data, opt_variables, loss_cfg, stage, reset_adam, begin=False):
+        if begin:            # get_parameter side effects happen once per optimize_main, not on every forward
+            PB.begin_stage_variables(data, self._layout, self._theta, self._flags, opt_variables)
+        pb = self._comp.compile(self._theta, opt_variables, loss_cfg, stage, p_begin=self._p_range[0], p_end=self._p_range[1],
+                                owner=(self.rank == 0), lbs_mode=0 if self.lbs_mode == 'full' else 1)
+        self._pb = pb
+        with torch.cuda.device(self.device):
+            if self._opt is None:
+                self._opt = ctypes.c_void_p()
+                L.check(self._lib.glamr_opt_create(ctypes.byref(self._opt), self.smpl.handle, ctypes.byref(pb)), 'glamr_opt_create')
+            else:
+                L.check(self._lib.glamr_opt_set_problem(self._opt, ctypes.byref(pb), int(reset_adam), L.stream_ptr()), 'glamr_opt_set_problem')
+
+    def _backward(self):
+        L.check(self._lib.glamr_opt_backward(self._opt, L.ptr(self._theta), L.ptr(self._reduce), L.stream_ptr()), 'glamr_opt_backward')
+        if self.world > 1:
+            torch.distributed.all_reduce(self._reduce)        # the one collective of the path: packed gradient + term sums
+
+    def _read(self, what, *shape):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        L.check(self._lib.glamr_opt_read(self._opt, what, ctypes.byref(p), ctypes.byref(n)), 'glamr_opt_read')
+        return _device_view(p.value, n.value, self.device).view(*shape).clone()
+
+    def _scatter_outputs(self, data):
+        """copy what forward() stores into the data dict in the reference (:421-528)"""
+        P, T, J = self._comp.P, self._comp.T, self._comp.J
+        ow, tw = self._read(L.R_ORIENT_WORLD, P, T, 3), self._read(L.R_TRANS_WORLD, P, T, 3)
+        ob, tb = self._read(L.R_ORIENT_BASE, P, T, 3), self._read(L.R_TRANS_BASE, P, T, 3)
+        kp = self._read(L.R_KP_PRED, P, T, J, 2)
+        ociw, tciw = self._read(L.R_ORIENT_CIW, P, T, 3), self._read(L.R_TRANS_CIW, P, T, 3)
+        tl = self._read(L.R_TRAJ_LOCAL, P, T, 11)
+        jw = self._read(L.R_JOINTS_WORLD, P, T, J, 3)
+        data['cam_pose'] = G.from34(self._read(L.R_CAM_POSE, T, 12))
+        data['cam_pose_inv'] = G.from34(self._read(L.R_CAM_POSE_INV, T, 12))
+        for p, d in enumerate(data['person_data'].values()):
+            d['smpl_orient_world'], d['root_trans_world'] = ow[p], tw[p]
+            d['smpl_orient_world_base'], d['root_trans_world_base'] = ob[p], tb[p]
+            d['kp_2d_pred'] = kp[p]
+            d['smpl_orient_cam_in_world'], d['root_trans_cam_in_world'] = ociw[p], tciw[p]
+            d['traj_local'] = tl[p][d['exist_frames']]
+            d['joints_world'] = jw[p]
+            d['person_transform_world'] = G.make_transform(ow[p], tw[p], 'axis_angle')
+
+    # ------------------------------------------------------------------------------------------------ reference API
+    def forward(self, data, opt_variables, opt_meta):
+        """:428-531 -- evaluates the current variables and refreshes the derived entries of `data`."""
+        with torch.cuda.device(self.device):
+            self._set_stage(data, opt_variables, getattr(self, '_loss_cfg', {}) or {}, opt_meta['stage'], reset_adam=False)
+            self._backward()
+            self._scatter_outputs(data)
+
+    def compute_loss(self, data, loss_cfg):
+        """:533-545 -> (total, weighted dict, unweighted dict) of 0-d CUDA tensors"""
+        with torch.cuda.device(self.device):
+            stage = getattr(self, '_cur_stage', 'opt')
+            self._set_stage(data, getattr(self, '_cur_vars', []), loss_cfg, stage, reset_adam=False)
+            self._backward()
+            L.check(self._lib.glamr_opt_losses(self._opt, L.ptr(self._reduce), L.ptr(self._terms), L.stream_ptr()), 'glamr_opt_losses')
+            terms = self._terms.clone()
+        uw = {name: terms[L.TERM_INDEX[name]] for name in loss_cfg}
+        wt = {name: uw[name] * loss_cfg[name]['weight'] for name in loss_cfg}
+        return terms[NUM_TERMS], wt, uw
+
+    def optimize_main(self, data, opt_variables, opt_lr, opt_niters, loss_cfg, opt_meta):
+        """:547-570 -- opt_niters fused iterations (forward + residuals + backward [+ allreduce] + Adam)."""
+        stage = opt_meta['stage']
+        self._cur_vars, self._cur_stage, self._loss_cfg = opt_variables, stage, loss_cfg
+        lib = self._lib
+        with torch.cuda.device(self.device):
+            self._set_stage(data, opt_variables, loss_cfg, stage, reset_adam=True, begin=True)
+            hist = torch.zeros((max(opt_niters, 1), NUM_TERMS + 1), device=self.device)
+            stream = torch.cuda.current_stream()
+
+            def one_iteration():
+                self._backward()
+                L.check(lib.glamr_opt_apply(self._opt, L.ptr(self._theta), L.ptr(self._reduce), float(opt_lr), L.ptr(hist), NUM_TERMS + 1,
+                                            L.stream_ptr()), 'glamr_opt_apply')
+            graph = None
+            done = 0
+            t_stage = time.time()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if opt_niters > 0:
+                one_iteration()                                  # warm-up (also sets kernel attributes) = iteration 0
+                done = 1
+                if self.use_cuda_graph and self.world == 1 and opt_niters > 2:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        one_iteration()
+                    # capture does not execute: the captured iteration still has to run
+            ev0.record()
+            chunk = max(int(self.log_interval), 1)
+            logged = 0
+            while done < opt_niters:
+                todo = min(chunk, opt_niters - done)
+                for _ in range(todo):
+                    if graph is not None:
+                        graph.replay()
+                    else:
+                        one_iteration()
+                done += todo
+                if self.log is not None or self.specs.get('print_logs', False):
+                    logged = self._write_logs(hist, logged, done, opt_niters, opt_lr, loss_cfg, stage, data['seq_name'], t_stage)
+            ev1.record()
+            ev1.synchronize()
+            if opt_niters > 1:
+                self.iter_ms.append((stage, opt_niters - 1, ev0.elapsed_time(ev1) / (opt_niters - 1)))
+            if self.log is not None or self.specs.get('print_logs', False):
+                self._write_logs(hist, logged, done, opt_niters, opt_lr, loss_cfg, stage, data['seq_name'], t_stage)
+            self.loss_history = hist
+            self.cur_iter = max(opt_niters - 1, 0)
+            if opt_niters > 0:
+                self._scatter_outputs(data)                      # state of the last closure, like the reference
+        return data
+
+    def _write_logs(self, hist, start, end, opt_niters, opt_lr, loss_cfg, stage, seq_name, t_stage):
+        """:646-659 same line format; values are read back in blocks of `log_interval` iterations."""
+        if end <= start:
+            return end
+        vals = hist[start:end].cpu().numpy()
+        per_iter = (time.time() - t_stage) / max(end, 1)
+        for k, it in enumerate(range(start, end)):
+            loss_str = ' | '.join(f'{name}: {vals[k, L.TERM_INDEX[name]]:7.3f}' for name in loss_cfg)
+            eta = _sec_to_time(per_iter * (opt_niters - it - 1))
+            info = f'{self.cfg.id} - {seq_name} - {stage} | {it:4d}/{opt_niters} | TE: {_sec_to_time(per_iter)} ETA: {eta} | LR: {opt_lr:.0e} | {loss_str}'
+            if self.log is None:
+                print(info)
+            else:
+                self.log.info(info)
+        return end
+
+    def optimize(self, in_dict, continue_opt=False):
+        """:572-589"""
+        if continue_opt:
+            data = tensor_to(in_dict, self.device)
+            self._attach(data)
+        else:
+            data = self.init_data(in_dict)
+        for stage, stage_specs in self.opt_stage_specs.items():
+            opt_meta = {'stage': stage, 'opt_latent_start_iter': stage_specs.get('opt_latent_start_iter', 0)}
+            self.optimize_main(data, stage_specs['opt_variables'], stage_specs['opt_lr'], stage_specs['opt_niters'],
+                               stage_specs['loss_cfg'], opt_meta)
+            if stage_specs.get('reinitialize_cam', False):
+                data['cam_pose'][:] = data['cam_pose'][[0]]
+                data['cam_pose_inv'] = G.inverse_transform(data['cam_pose'])
+        out = tensor_to_numpy(data)
+        return out
+
+
+def _device_view(addr, count, device):
+    """float32 tensor aliasing `count` floats of device memory at `addr` (owned by a CUDA-library handle)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {'shape': (count,), 'typestr': '<f4', 'data': (addr, False), 'version': 2}
+    return torch.as_tensor(h, device=device)

@@ -143,3 +143,32 @@ def make_in_dict(assets, num_persons, num_fr, seed=0, gaps=False, seq_name='synt
         exist = make_exist_with_gaps(num_fr, seed=seed * 31 + p) if gaps else None
         est[p] = make_pose_dict(assets, p, num_fr, seed=seed, exist=exist)
     return {'est': est, 'gt': {}, 'gt_meta': {}, 'seq_name': seq_name}
+
+
+class SyntheticPrior:
+    """Stand-in for the learned motion/trajectory prior with the ``MotionTrajJointModel.inference`` contract
+    (motion_infiller/models/motion_traj_joint_model.py:141-145): returns the input body pose as the "infilled" pose
+    and a smooth seeded 11-D local trajectory.  Used only to seed benchmark problems when no network weights exist;
+    both the CUDA arm and the CPU reference arm of bench.py consume the same instance's outputs."""
+
+    def __init__(self, seed=0, device='cpu'):
+        self.seed, self.device, self.calls = seed, device, 0
+
+    def inference(self, batch, sample_num=1):
+        import torch
+        pose = batch['in_body_pose']
+        B, T = pose.shape[0], pose.shape[1]
+        rng = np.random.default_rng(self.seed + 17 * self.calls)
+        self.calls += 1
+        local = np.zeros((T, B, 11), np.float32)
+        local[..., 0:2] = rng.normal(0.0, 0.01, (T, B, 2))
+        local[..., 2] = 0.9 + np.cumsum(rng.normal(0.0, 0.002, (T, B)), axis=0)
+        d6 = np.array([1.0, 0.0, 0.0, 0.0, 1.0, 0.0]) + np.cumsum(rng.normal(0.0, 0.01, (T, B, 6)), axis=0)
+        local[..., 3:9] = d6
+        dh = rng.normal(0.0, 0.02, (T, B))
+        local[..., 9], local[..., 10] = np.cos(dh), np.sin(dh)
+        t = lambda a: torch.tensor(a, dtype=torch.float32, device=self.device)
+        return {'infer_out_body_pose': pose.to(torch.float32).reshape(B, 1, T, 69).clone(),
+                'infer_out_local_traj_tp': t(local).reshape(T, B, 1, 11),
+                'infer_out_orient': torch.zeros((B, 1, T, 3), dtype=torch.float32, device=self.device),
+                'infer_out_trans': torch.zeros((B, 1, T, 3), dtype=torch.float32, device=self.device)}

@@ -189,6 +189,12 @@ int glamr_opt_apply(glamr_opt_t* st, float* theta, const float* reduce_buf, doub
 /* loss_terms only, no update (GlobalReconOptimizer.compute_loss, :533-545) */
 int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms, void* stream);
 
+/* Measurement hooks (bench.py roofline): when enabled, glamr_opt_backward brackets the LBS kernel with CUDA events on
+ * the launching stream (do not enable while capturing a CUDA graph); glamr_opt_last_lbs_ms waits for the last pair
+ * and returns its duration.  The only entry point that synchronises. */
+int glamr_opt_kernel_timing(glamr_opt_t* st, int enable);
+int glamr_opt_last_lbs_ms(glamr_opt_t* st, float* ms);
+
 enum glamr_read {
   GLAMR_R_ORIENT_WORLD = 0,    /* [P,T,3]   smpl_orient_world            */
   GLAMR_R_TRANS_WORLD = 1,     /* [P,T,3]   root_trans_world             */

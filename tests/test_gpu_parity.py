@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C-ABI library) against the oracle and the reference-generated golden
+fixtures.  Runs on the B200 box:  python -m pytest tests -m gpu"""
+import copy
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GLOBALOPT_CASES, ReplayMT, case_setup, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _cuda(x):
+    return torch.tensor(x, device=DEV)
+
+
+# ------------------------------------------------------------------------------------------------ rotation algebra
+def test_rowops_match_reference_golden():
+    from glamr_b200 import geometry as G
+    g = load_golden('rotations')
+    aa, d6, R, q, qn, q2, y, x = [_cuda(g[k]) for k in ['in_aa', 'in_d6', 'in_R', 'in_q', 'in_qn', 'in_q2', 'in_y', 'in_x']]
+    M = G.make_transform(aa, d6[:, :3].contiguous(), 'axis_angle')
+    got = {
+        'aa_to_rotmat': G.angle_axis_to_rotation_matrix(aa), 'rotmat_to_quat': G.rotation_matrix_to_quaternion(R),
+        'quat_to_aa': G.quaternion_to_angle_axis(qn), 'quat_to_aa_raw': G.quaternion_to_angle_axis(q),
+        'aa_to_quat': G.angle_axis_to_quaternion(aa), 'quat_to_rotmat': G.quaternion_to_rotation_matrix(q),
+        'rotmat_to_aa': G.rotation_matrix_to_angle_axis(R), 'quat_mul': G.quat_mul(qn, q2), 'quat_angle_diff': G.quat_angle_diff(qn, q2),
+        'safe_atan2': G.safe_atan2(y, x), 'rot6d_to_rotmat': G.rot6d_to_rotmat(d6), 'aa_to_rot6d': G.angle_axis_to_rot6d(aa),
+        'rot6d_to_quat': G.rot6d_to_quat(d6), 'get_heading': G.get_heading(qn), 'get_heading_q': G.get_heading_q(qn),
+        'heading_to_quat': G.heading_to_quat(y), 'deheading_quat': G.deheading_quat(qn), 'make_transform_aa': M,
+        'inverse_transform': G.inverse_transform(M), 'transform_rot': G.transform_rot(M, aa.flip(0).contiguous()),
+        'transform_trans': G.transform_trans(M, d6[:, 3:].contiguous()),
+    }
+    for k, v in got.items():
+        np.testing.assert_allclose(v.cpu().numpy(), g[k], rtol=0, atol=5e-6, err_msg=k)
+
+
+def test_rowop_vjps_match_autograd():
+    from glamr_b200 import lib as L
+    from oracle import rotations as rt
+    from oracle.smpl import rodrigues_smplx
+    gen = torch.Generator().manual_seed(1)
+    aa = torch.randn(512, 3, generator=gen)
+    aa[:16] *= 1e-4
+    aa[16:20] = 0.0
+    cases = [(L.ROP_AA_TO_ROTMAT, aa, lambda a: rt.aa_to_rotmat(a).reshape(-1, 9)),
+             (L.ROP_AA_TO_QUAT, aa, rt.aa_to_quat),
+             (L.ROP_RODRIGUES_SMPLX, aa[20:], lambda a: rodrigues_smplx(a).reshape(-1, 9)),
+             (L.ROP_ROT6D_TO_ROTMAT, torch.randn(512, 6, generator=gen), lambda a: rt.rot6d_to_rotmat(a).reshape(-1, 9)),
+             (L.ROP_QUAT_TO_AA, torch.nn.functional.normalize(torch.randn(512, 4, generator=gen), dim=-1), rt.quat_to_aa),
+             (L.ROP_ROTMAT_TO_AA, (rt.aa_to_rotmat(torch.randn(512, 3, generator=gen)) + 1e-3 * torch.randn(512, 3, 3, generator=gen)).reshape(-1, 9),
+              lambda a: rt.rotmat_to_aa(a.reshape(-1, 3, 3)))]
+    for op, a, fn in cases:
+        a = a.clone().requires_grad_(True)
+        ref = fn(a)
+        go = torch.randn(ref.shape, generator=gen)
+        (gref,) = torch.autograd.grad(ref, a, go)
+        out = L.rowop(op, a.detach().to(DEV))
+        np.testing.assert_allclose(out.cpu().numpy(), ref.detach().numpy(), atol=5e-6, err_msg=f'op {op} fwd')
+        ga, _ = L.rowop_vjp(op, a.detach().to(DEV), None, go.to(DEV))
+        scale = np.maximum(np.abs(gref.numpy()).max(axis=1, keepdims=True), 1.0)
+        assert (np.abs(ga.cpu().numpy() - gref.numpy()) / scale).max() < 3e-4, f'op {op} vjp'
+
+
+# ------------------------------------------------------------------------------------------------ SMPL
+def test_smpl_forward_matches_reference_golden(smpl_assets):
+    from glamr_b200.smpl import SMPL
+    g = load_golden('smpl')
+    smpl = SMPL(smpl_assets, pose_type='body26fk', device=DEV)
+    o, p, b, t, s = [_cuda(g[k]) for k in ['in_orient', 'in_pose', 'in_betas', 'in_trans', 'in_scale']]
+    vsel = g['vsel']
+    out = smpl(global_orient=o, body_pose=p, betas=b, root_trans=t)
+    np.testing.assert_allclose(out.joints.cpu().numpy(), g['joints'], atol=1e-4)       # north-star bound; expect ~1e-6
+    assert np.abs(out.joints.cpu().numpy() - g['joints']).max() < 2e-5
+    np.testing.assert_allclose(out.vertices[:, vsel].cpu().numpy(), g['verts_sel'], atol=2e-5)
+    np.testing.assert_allclose(out.vertices.double().sum(1).cpu().numpy(), g['verts_sum'], atol=5e-3)
+    np.testing.assert_allclose(out.vertices.double().abs().sum(1).cpu().numpy(), g['verts_abs_sum'], rtol=2e-6)
+    out = smpl(global_orient=o, body_pose=p, betas=b, root_trans=t, root_scale=s)
+    np.testing.assert_allclose(out.joints.cpu().numpy(), g['joints_scaled'], atol=2e-5)
+    np.testing.assert_allclose(out.vertices[:, vsel].cpu().numpy(), g['verts_scaled_sel'], atol=2e-5)
+    out = smpl(global_orient=o, body_pose=p, betas=b)
+    np.testing.assert_allclose(out.joints.cpu().numpy(), g['joints_raw'], atol=2e-5)
+    np.testing.assert_allclose(out.vertices[:, vsel].cpu().numpy(), g['verts_raw_sel'], atol=2e-5)
+    out = smpl(global_orient=o, body_pose=p, betas=b, root_trans=t, orig_joints=True)
+    np.testing.assert_allclose(out.joints.cpu().numpy(), g['joints24'], atol=2e-5)
+    np.testing.assert_allclose(out.vertices[:, vsel].cpu().numpy(), g['verts24_sel'], atol=2e-5)
+    np.testing.assert_allclose(smpl.get_joints(body_pose=p, global_orient=o, root_trans=t).cpu().numpy(), g['fk_joints'], atol=2e-5)
+
+
+@pytest.mark.parametrize('n', [1, 31, 32, 33, 300, 1000])
+def test_smpl_forward_matches_oracle_ragged_sizes(n, smpl_assets):
+    """frame counts around the 32-frame CTA tile, all 6890 vertices compared"""
+    from glamr_b200.smpl import SMPL
+    from oracle.smpl import OracleSMPL
+    smpl = SMPL(smpl_assets, pose_type='body26fk', device=DEV)
+    ora = OracleSMPL(smpl_assets)
+    gen = torch.Generator().manual_seed(n)
+    o, p = torch.randn(n, 3, generator=gen), torch.randn(n, 69, generator=gen) * 0.4
+    b, t = torch.randn(n, 10, generator=gen), torch.randn(n, 3, generator=gen)
+    out = smpl(global_orient=o.to(DEV), body_pose=p.to(DEV), betas=b.to(DEV), root_trans=t.to(DEV))
+    m = min(n, 64)
+    j, v = ora(o[:m], p[:m], b[:m], root_trans=t[:m])
+    assert (out.joints[:m].cpu() - j).abs().max() < 2e-5
+    assert (out.vertices[:m].cpu() - v).abs().max() < 2e-5
+    if n > 64:
+        j, v = ora(o[-8:], p[-8:], b[-8:], root_trans=t[-8:])
+        assert (out.joints[-8:].cpu() - j).abs().max() < 2e-5
+        assert (out.vertices[-8:].cpu() - v).abs().max() < 2e-5
+
+
+def test_smpl_dense_skinning_model(smpl_assets):
+    """a model whose skinning weights are dense (24 per vertex) takes the generic-K kernel"""
+    from glamr_b200.smpl import SMPL
+    from oracle.smpl import OracleSMPL
+    a = dict(smpl_assets)
+    rng = np.random.default_rng(5)
+    w = rng.random((6890, 24)).astype(np.float32)
+    a['lbs_weights'] = w / w.sum(1, keepdims=True)
+    smpl, ora = SMPL(a, device=DEV), OracleSMPL(a)
+    gen = torch.Generator().manual_seed(0)
+    o, p, b, t = torch.randn(5, 3, generator=gen), torch.randn(5, 69, generator=gen) * 0.3, torch.randn(5, 10, generator=gen), torch.randn(5, 3, generator=gen)
+    out = smpl(global_orient=o.to(DEV), body_pose=p.to(DEV), betas=b.to(DEV), root_trans=t.to(DEV))
+    j, v = ora(o, p, b, root_trans=t)
+    assert (out.joints.cpu() - j).abs().max() < 2e-5 and (out.vertices.cpu() - v).abs().max() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ global optimisation
+def _make(name, smpl_assets, **spec_over):
+    from glamr_b200.recon import GlobalReconOptimizer
+    gold, cfg, in_dict = case_setup(name, smpl_assets)
+    cfg.grecon_model_specs.update(spec_over)
+    model = GlobalReconOptimizer(cfg, torch.device(DEV), None, smpl=smpl_assets, mt_model=ReplayMT(gold, DEV))
+    return gold, cfg, in_dict, model
+
+
+@pytest.mark.parametrize('name', GLOBALOPT_CASES)
+def test_globalopt_matches_reference_golden(name, smpl_assets):
+    """init state, iteration-0 gradients, per-iteration residual values and final poses vs the executed reference"""
+    from glamr_b200 import lib as L
+    gold, cfg, in_dict, model = _make(name, smpl_assets)
+    data = model.init_data(copy.deepcopy(in_dict))
+    for p, (pid, pd) in enumerate(data['person_data'].items()):
+        np.testing.assert_allclose(pd['kp_2d_pred'].cpu().numpy(), gold[f'init/{pid}/kp_2d_pred'], atol=5e-3, err_msg='init kp')
+        np.testing.assert_allclose(pd['smpl_orient_world'].cpu().numpy(), gold[f'init/{pid}/smpl_orient_world'], atol=1e-4)
+        np.testing.assert_allclose(pd['root_trans_world'].cpu().numpy(), gold[f'init/{pid}/root_trans_world'], atol=1e-4)
+        np.testing.assert_allclose(pd['traj_local_pred'].cpu().numpy(), gold[f'init/{pid}/traj_local_pred'], atol=1e-5)
+    np.testing.assert_allclose(data['cam_pose'].cpu().numpy(), gold['init/cam_pose'], atol=1e-5)
+    for stage, specs in cfg.opt_stage_specs.items():
+        n = specs['opt_niters']
+        model.optimize_main(data, specs['opt_variables'], specs['opt_lr'], n, specs['loss_cfg'], {'stage': stage})
+        hist = model.loss_history.cpu().numpy()
+        for k in specs['loss_cfg']:
+            ref = gold[f'loss/{stage}/{k}']
+            np.testing.assert_allclose(hist[:n, L.TERM_INDEX[k]], ref, rtol=3e-3, atol=1e-5, err_msg=f'{stage} {k}')
+    T = data['seq_len']
+    for pid, pd in data['person_data'].items():
+        for k, tol in [('smpl_orient_world', 2e-3), ('root_trans_world', 2e-3), ('traj_local_xy', 1e-3)]:
+            np.testing.assert_allclose(pd[k].cpu().numpy().reshape(gold[f'final/{pid}/{k}'].shape), gold[f'final/{pid}/{k}'], atol=tol,
+                                       err_msg=f'final {pid} {k}')
+    np.testing.assert_allclose(data['cam_pose'].cpu().numpy(), gold['final/cam_pose'], atol=2e-3)
+
+
+@pytest.mark.parametrize('name', ['dynamic_p1_t40', 'static_multi_p3_t30', '3dpw_p2_t80_gaps'])
+def test_globalopt_gradients_match_oracle_autograd(name, smpl_assets):
+    """first closure of every stage: every variable's gradient vs torch autograd through the full-LBS oracle"""
+    from glamr_b200 import lib as L
+    from oracle.global_opt import OracleGlobalRecon
+    gold, cfg, in_dict, model = _make(name, smpl_assets)
+    data = model.init_data(copy.deepcopy(in_dict))
+    ora = OracleGlobalRecon(copy.deepcopy(cfg), smpl_assets, mt_model=ReplayMT(gold))
+    data_o = ora.init_data(copy.deepcopy(in_dict))
+    for stage, specs in cfg.opt_stage_specs.items():
+        params = ora.get_parameter(data_o, specs['opt_variables'])
+        for p_ in params:
+            p_.requires_grad_(True)
+            p_.grad = None
+        ora.forward(data_o, specs['opt_variables'], {'stage': stage})
+        total, _, uw = ora.compute_loss(data_o, specs['loss_cfg'])
+        total.backward()
+        model._cur_vars, model._cur_stage = specs['opt_variables'], stage
+        model._set_stage(data, specs['opt_variables'], specs['loss_cfg'], stage, reset_adam=True, begin=True)
+        model._backward()
+        grad = model._reduce[:model._layout.n_params].cpu()
+        lay = model._layout
+        gv = lay.views(grad)
+        order = []
+        if 'cam' not in specs['opt_variables']:
+            order += [gv['cam_inv_rot_residual'], gv['cam_inv_trans_residual']]
+        elif model.flag_fixed_cam:
+            order += [gv['cam_rot_6d_fix'], gv['cam_trans_fix']]
+        else:
+            order += [gv['cam_rot_6d'], gv['cam_trans']]
+        for p in range(len(data['person_data'])):
+            pv = lay.views(grad, p)
+            for key in specs['opt_variables']:
+                if 'local' in key:
+                    order.append(pv[f'traj_{key}'])
+            if 'world_dheading' in specs['opt_variables']:
+                order.append(pv['world_dheading'])
+        assert len(order) == len(params)
+        for i, (g_, p_) in enumerate(zip(order, params)):
+            if p_.grad is None:
+                continue
+            scale = max(float(p_.grad.abs().max()), 1e-9)
+            err = float((g_.reshape(p_.grad.shape) - p_.grad).abs().max()) / scale
+            assert err < 5e-4, f'{stage} param {i}: rel err {err:.2e}'
+        for p_ in params:
+            p_.requires_grad_(False)
+        # advance both by the stage so the next stage starts from comparable states
+        ora.optimize_main(data_o, specs['opt_variables'], specs['opt_lr'], specs['opt_niters'], specs['loss_cfg'], {'stage': stage})
+        model.optimize_main(data, specs['opt_variables'], specs['opt_lr'], specs['opt_niters'], specs['loss_cfg'], {'stage': stage})
+
+
+def test_optimize_output_layout_and_oracle_parity(smpl_assets):
+    """optimize() end to end: output keys/dtypes of the reference and joints/vertices/camera
+    within 1e-4 of the oracle recomputed from the returned SMPL parameters (north-star parity statement)."""
+    from glamr_b200.smpl import SMPL
+    from oracle.global_opt import OracleGlobalRecon
+    from oracle.smpl import OracleSMPL
+    gold, cfg, in_dict, model = _make('dynamic_p1_t40', smpl_assets)
+    out = model.optimize(copy.deepcopy(in_dict))
+    ora = OracleGlobalRecon(copy.deepcopy(cfg), smpl_assets, mt_model=ReplayMT(gold))
+    ref = ora.optimize(copy.deepcopy(in_dict))
+    pd, pr = out['person_data'][0], ref['person_data'][0]
+    for k in ['smpl_pose', 'smpl_beta', 'smpl_orient_world', 'root_trans_world', 'scale', 'cam_K', 'exist_frames', 'vis_frames',
+              'invis_frames', 'visible_orig', 'frames', 'frame2ind', 'max_len', 'kp_2d_pred', 'traj_local_rot', 'world_dheading']:
+        assert k in pd, k
+    for k in ['cam_pose', 'cam_pose_inv', 'seq_len', 'meta', 'gt', 'gt_meta', 'cam_rot_6d', 'cam_trans', 'rel_transform_cam']:
+        assert k in out, k
+    assert pd['kp_2d'].dtype == np.float64 and pd['kp_2d_pred'].dtype == np.float32 and pd['vis_frames'].dtype == np.bool_
+    assert out['cam_pose'].shape == (40, 4, 4) and pd['smpl_orient_world'].shape == (40, 3)
+    np.testing.assert_allclose(out['cam_pose'], ref['cam_pose'], atol=1e-4)
+    np.testing.assert_allclose(out['cam_pose_inv'], ref['cam_pose_inv'], atol=1e-4)
+    # joints / vertices from the returned SMPL parameters, CUDA vs oracle SMPL on the ORACLE's parameters
+    smpl = SMPL(smpl_assets, device=DEV)
+    o = smpl(global_orient=_cuda(pd['smpl_orient_world']), body_pose=_cuda(pd['smpl_pose']), betas=_cuda(pd['smpl_beta']),
+             root_trans=_cuda(pd['root_trans_world']), orig_joints=True)
+    jr, vr = OracleSMPL(smpl_assets)(torch.tensor(pr['smpl_orient_world']), torch.tensor(pr['smpl_pose']), torch.tensor(pr['smpl_beta']),
+                                     root_trans=torch.tensor(pr['root_trans_world']), orig_joints=True)
+    assert (o.joints.cpu() - jr).abs().max() < 2e-3      # after 6 Adam steps; per-step parity is covered above
+    assert (o.vertices.cpu() - vr).abs().max() < 2e-3
+
+
+def test_cuda_graph_and_eager_iterations_agree(smpl_assets):
+    outs = []
+    for graph in (True, False):
+        gold, cfg, in_dict, model = _make('static_multi_p3_t30', smpl_assets, use_cuda_graph=graph)
+        outs.append(model.optimize(copy.deepcopy(in_dict)))
+    for pid in outs[0]['person_data']:
+        np.testing.assert_array_equal(outs[0]['person_data'][pid]['smpl_orient_world'], outs[1]['person_data'][pid]['smpl_orient_world'])
+    np.testing.assert_array_equal(outs[0]['cam_pose'], outs[1]['cam_pose'])
+
+
+def test_product_fails_loudly_on_cpu_device(smpl_assets):
+    from glamr_b200.lib import GlamrError
+    from glamr_b200.recon import GlobalReconOptimizer
+    gold, cfg, in_dict = case_setup('static_p1_t24', smpl_assets)
+    with pytest.raises(GlamrError):
+        GlobalReconOptimizer(cfg, torch.device('cpu'), None, smpl=smpl_assets, mt_model=ReplayMT(gold))
