@@ -1,0 +1,224 @@
+"""Learned motion / trajectory prior on the CUDA library -- drop-in for the inference surface of the reference's
+``MotionTrajJointModel`` (motion_infiller/models/motion_traj_joint_model.py:17-145): ``inference(batch, sample_num)``,
+``get_motion_latent``, ``get_traj_latent``.
+
+The networks run in ``glamr_infiller_window_forward`` / ``glamr_trajpred_forward`` (glamr_b200/csrc/nets_kernels.cu);
+this module only slices the 50-frame windows (autoregressive over windows exactly like
+MotionInfillerVAE.inference_multi_step, motion_infiller_vae.py:618-632, but batched over ALL sequences instead of the
+reference's batch of one), runs SMPL FK for the joint-position features and reshapes the outputs into the reference's
+dict layout.  Weights come from the reference's Lightning checkpoints (state_dict names are kept) or from an explicit
+state dict; there is no CPU fallback.
+"""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+PAST, CUR, FUT, NZ = 10, 30, 10, 128
+WINDOW = PAST + CUR + FUT
+
+
+def _declare(lib):
+    if getattr(lib, '_nets_declared', False):
+        return
+    lib.glamr_infiller_workspace_floats.restype = ctypes.c_size_t
+    lib.glamr_trajpred_workspace_floats.restype = ctypes.c_size_t
+    lib.glamr_net_set_tensor.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+    lib.glamr_infiller_window_forward.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p,
+                                                                                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.glamr_trajpred_forward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + \
+        [ctypes.c_void_p] * 6 + [ctypes.c_size_t, ctypes.c_void_p]
+    lib._nets_declared = True
+
+
+class _Net:
+    """opaque glamr_net_t with the parameters of one network"""
+
+    def __init__(self, state, device):
+        self.device = L.require_cuda(device)
+        self.lib = L.load()
+        _declare(self.lib)
+        self.h = ctypes.c_void_p()
+        L.check(self.lib.glamr_net_create(ctypes.byref(self.h)), 'glamr_net_create')
+        with torch.cuda.device(self.device):
+            for name, val in state.items():
+                arr = np.ascontiguousarray(val.detach().cpu().numpy() if isinstance(val, torch.Tensor) else np.asarray(val), dtype=np.float32)
+                if arr.size == 0 or arr.dtype != np.float32:
+                    continue
+                L.check(self.lib.glamr_net_set_tensor(self.h, name.encode(), arr.ctypes.data_as(ctypes.c_void_p), arr.size), f'set_tensor {name}')
+        self._ws = None
+
+    def workspace(self, floats):
+        if self._ws is None or self._ws.numel() < floats:
+            self._ws = torch.empty(int(floats), dtype=torch.float32, device=self.device)
+        return self._ws
+
+    def __del__(self):
+        try:
+            self.lib.glamr_net_destroy(self.h)
+        except Exception:
+            pass
+
+
+class MotionInfillerVAE:
+    """inference surface of motion_infiller/models/motion_infiller_vae.py:440-667 (pose_rep 'body', axis-angle)"""
+    model_type = 'angle'
+
+    def __init__(self, state, device):
+        self.net = _Net(state, device)
+        self.device = self.net.device
+        self.nz, self.past_nframe, self.cur_nframe, self.fut_nframe = NZ, PAST, CUR, FUT
+
+    def get_latent(self, seq_len):
+        return torch.randn((int(np.ceil((seq_len - PAST) / CUR)), NZ))
+
+    def inference(self, batch, sample_num=1, recon=False, multi_step=True):
+        if recon or not multi_step:
+            raise NotImplementedError('only the multi-step sampling path (recon=False) is implemented on CUDA')
+        dev = self.device
+        pose_in = batch['in_body_pose'].to(dev, torch.float32)
+        B0, T = pose_in.shape[:2]
+        pose = pose_in.repeat_interleave(sample_num, dim=0).transpose(0, 1).contiguous().clone()       # [T,B,69]
+        key_pad_all = ~(batch['frame_mask'].to(dev) == 1)
+        key_pad_all = key_pad_all.repeat_interleave(sample_num, dim=0)
+        B = B0 * sample_num
+        lib = self.net.lib
+        ws = self.net.workspace(lib.glamr_infiller_workspace_floats(B))
+        out = torch.empty((PAST + CUR, B, 69), dtype=torch.float32, device=dev)
+        pieces = []
+        nwin = int(np.ceil((T - PAST) / CUR))
+        latent = batch.get('in_motion_latent')
+        with torch.cuda.device(dev):
+            for i in range(nwin):
+                s, e = i * CUR, i * CUR + WINDOW
+                eb = min(e, T)
+                win = torch.zeros((WINDOW, B, 69), dtype=torch.float32, device=dev)
+                win[:eb - s] = pose[s:eb]
+                kp = torch.ones((B, WINDOW), dtype=torch.uint8, device=dev)
+                kp[:, :eb - s] = key_pad_all[:, s:eb].to(torch.uint8)
+                kp[:, :PAST] = 0
+                if latent is not None:
+                    eps, rows = latent[[i]].to(dev, torch.float32).contiguous(), 1
+                else:
+                    eps, rows = torch.randn((B, NZ), device=dev), B
+                L.check(lib.glamr_infiller_window_forward(self.net.h, B, win.data_ptr(), kp.data_ptr(), eps.data_ptr(), rows, out.data_ptr(),
+                                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+                        'glamr_infiller_window_forward')
+                nfr = min(e - FUT, T) - s
+                pose[s:s + nfr] = out[:nfr]
+                pieces.append(out[:nfr].clone() if i == 0 else out[PAST:nfr].clone())
+        body = torch.cat(pieces, dim=0).transpose(0, 1).reshape(B0, sample_num, T, 69).contiguous()
+        data = dict(batch)
+        data['infer_out_body_pose'] = body
+        data['infer_out_pose'] = torch.cat([torch.zeros_like(body[..., :3]), body], dim=-1)
+        data['batch_size'], data['seq_len'] = B0, T
+        return data
+
+
+class TrajPredVAE:
+    """inference surface of traj_pred/models/traj_pred_vae.py:341-548 (6d local orientation, joint-position input)"""
+    model_type = 'joint'
+    in_joint_pos_only = False
+
+    def __init__(self, state, device, smpl):
+        self.net = _Net(state, device)
+        self.device, self.smpl, self.nz = self.net.device, smpl, NZ
+
+    def get_latent(self, seq_len):
+        return torch.zeros((1, NZ))
+
+    def get_joint_pos(self, body_pose):
+        """:384-394  23 FK joints (root removed), zero orientation, rest joints from v_template"""
+        flat = body_pose.reshape(-1, 69).to(self.device, torch.float32).contiguous()
+        z3 = torch.zeros((flat.shape[0], 3), device=self.device)
+        joints = self.smpl.get_joints(global_orient=z3, body_pose=flat, root_trans=z3)
+        return joints[:, 1:, :].reshape(body_pose.shape[:-1] + (69,))
+
+    def inference(self, batch, sample_num=1, recon=False, recon_only=False, multi_step=False):
+        if recon or recon_only or multi_step or sample_num != 1:
+            raise NotImplementedError('only single-pass sampling (multi_step_trajpred=false, sample_num=1) is implemented on CUDA')
+        dev = self.device
+        body = batch['in_body_pose'].to(dev, torch.float32)                       # [B,T,69]
+        B, T = body.shape[:2]
+        jp = self.get_joint_pos(body).transpose(0, 1).contiguous()                # [T,B,69]
+        lib = self.net.lib
+        ws = self.net.workspace(lib.glamr_trajpred_workspace_floats(T, B))
+        local = torch.empty((T, B, 11), dtype=torch.float32, device=dev)
+        trans = torch.empty((T, B, 3), dtype=torch.float32, device=dev)
+        orient = torch.empty((T, B, 3), dtype=torch.float32, device=dev)
+        latent = batch.get('in_traj_latent')
+        if latent is not None:
+            eps = latent.to(dev, torch.float32).contiguous()
+            rows = 1 if eps.shape[0] == 1 else B
+        else:
+            eps, rows = torch.randn((B, NZ), device=dev), B
+        ixy = batch['init_xy'].to(dev, torch.float32).contiguous() if 'init_xy' in batch else None
+        ih = batch['init_heading'].to(dev, torch.float32).contiguous() if 'init_heading' in batch else None
+        with torch.cuda.device(dev):
+            L.check(lib.glamr_trajpred_forward(self.net.h, T, B, jp.data_ptr(), eps.data_ptr(), rows, None if ixy is None else ixy.data_ptr(),
+                                               None if ih is None else ih.data_ptr(), local.data_ptr(), trans.data_ptr(), orient.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), 'glamr_trajpred_forward')
+        out = {'infer_out_local_traj_tp': local.view(T, B, 1, 11), 'infer_out_trans_tp': trans.view(T, B, 1, 3),
+               'infer_out_orient_tp': orient.view(T, B, 1, 3)}
+        out['infer_out_orient'] = out['infer_out_orient_tp'].permute(1, 2, 0, 3).contiguous()
+        out['infer_out_trans'] = out['infer_out_trans_tp'].permute(1, 2, 0, 3).contiguous()
+        out['infer_out_pose'] = torch.cat([out['infer_out_orient'], body.unsqueeze(1)], dim=-1)
+        return out
+
+
+def _find_checkpoint(cfg_dir, cp='best'):
+    """results/<cfg>/version_N/checkpoints/*best*.ckpt (lib/utils/tools.py:41-45,94-104)"""
+    versions = sorted(glob.glob(os.path.join(cfg_dir, 'version_*')), key=lambda p: int(p.rsplit('_', 1)[1]))
+    if not versions:
+        raise FileNotFoundError(f'no checkpoint versions under {cfg_dir}')
+    files = glob.glob(os.path.join(versions[-1], 'checkpoints', f'*{cp}*.ckpt'))
+    if not files:
+        raise FileNotFoundError(f'no *{cp}*.ckpt under {versions[-1]}/checkpoints')
+    return files[0]
+
+
+class MotionTrajJointModel:
+
+    def __init__(self, cfg=None, device=torch.device('cuda'), log=None, smpl=None, states=None):
+        """cfg: config id / object of the joint model (only its checkpoint locations are used).  states: optional
+        (infiller_state_dict, trajpred_state_dict); otherwise the reference's checkpoint files are loaded."""
+        self.cfg, self.device, self.log = cfg, L.require_cuda(device), log
+        self.multi_step_mfiller, self.multi_step_trajpred = True, False
+        if smpl is None:
+            from .smpl import SMPL
+            smpl = SMPL(device=self.device)
+        self.smpl = smpl
+        if states is None:
+            states = []
+            for sub in ['results/motion_filler/motion_infiller_demo', 'results/traj_pred/traj_pred_demo']:
+                ck = torch.load(_find_checkpoint(sub), map_location='cpu', weights_only=False)
+                states.append(ck.get('state_dict', ck))
+        self.mfiller = MotionInfillerVAE(states[0], self.device)
+        self.traj_predictor = TrajPredVAE(states[1], self.device, self.smpl)
+
+    def get_motion_latent(self, seq_len):
+        return self.mfiller.get_latent(seq_len)
+
+    def get_traj_latent(self, seq_len):
+        return self.traj_predictor.get_latent(seq_len)
+
+    def inference(self, batch, sample_num=1, recon=False):
+        """motion_traj_joint_model.py:141-145 (+ pred_trajectory :73-133, 'infer' mode)"""
+        if recon:
+            raise NotImplementedError('recon mode needs the posterior encoders (training-side, out of scope)')
+        data = self.mfiller.inference(batch, sample_num, recon=False, multi_step=True)
+        motion = data['infer_out_body_pose']                                        # [B,S,T,69]
+        B, S, T = motion.shape[:3]
+        tb = {'in_body_pose': motion.reshape(B * S, T, 69)}
+        if 'in_traj_latent' in data:
+            tb['in_traj_latent'] = data['in_traj_latent']
+        out = self.traj_predictor.inference(tb, sample_num=1)
+        data['infer_out_pose'] = out['infer_out_pose'].view(B, S, T, 72)
+        data['infer_out_trans'] = out['infer_out_trans'].view(B, S, T, 3)
+        data['infer_out_orient'] = out['infer_out_orient'].view(B, S, T, 3)
+        data['infer_out_local_traj_tp'] = out['infer_out_local_traj_tp'].view(T, B, S, 11)
+        return data

@@ -86,6 +86,33 @@ int glamr_traj_local2global(int T, int B, const float* local_traj, int local_hea
                             float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Learned prior (inference only)  --  stands behind MotionTrajJointModel.inference
+ * (motion_infiller/models/motion_traj_joint_model.py:141-145): MotionInfillerVAE.inference_one_step
+ * (motion_infiller/models/motion_infiller_vae.py:551-562 with ContextEncoder :92-123, DataDecoder :345-421) and
+ * TrajPredVAE.inference (traj_pred/models/traj_pred_vae.py:524-548 with ContextEncoder :72-92, DataDecoder :269-333).
+ * Parameters are registered under their reference state-dict names ("context_encoder.in_fc.weight", ...), so a
+ * Lightning checkpoint's state_dict maps 1:1.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct glamr_net glamr_net_t;
+int glamr_net_create(glamr_net_t** out);
+int glamr_net_destroy(glamr_net_t* n);
+/* upload one named float32 parameter from a HOST pointer */
+int glamr_net_set_tensor(glamr_net_t* n, const char* name, const float* host, size_t numel);
+size_t glamr_infiller_workspace_floats(int B);
+size_t glamr_trajpred_workspace_floats(int T, int B);
+/* One 50-frame window (past 10 | current 30 | future 10), B sequences, seq-first buffers:
+ *   in_pose [50,B,69]   key_pad_mask [B,50] uint8 (1 = frame invisible / padding)   eps [eps_rows,128], eps_rows in {1,B}, or NULL
+ *   out_pose [40,B,69] = the 10 past input frames followed by the 30 decoded frames */
+int glamr_infiller_window_forward(const glamr_net_t* n, int B, const float* in_pose, const uint8_t* key_pad_mask,
+                                  const float* eps, int eps_rows, float* out_pose, float* workspace, size_t workspace_floats,
+                                  void* stream);
+/*   in_joint_pos [T,B,69] (23 joints from SMPL.get_joints)   eps as above   init_xy [B,2] / init_heading [B] or NULL
+ *   out_local_traj [T,B,11]   out_trans [T,B,3]   out_orient_aa [T,B,3] */
+int glamr_trajpred_forward(const glamr_net_t* n, int T, int B, const float* in_joint_pos, const float* eps, int eps_rows,
+                           const float* init_xy, const float* init_heading, float* out_local_traj, float* out_trans,
+                           float* out_orient_aa, float* workspace, size_t workspace_floats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Global optimisation  --  stands behind GlobalReconOptimizer.forward / compute_loss / optimize_main
  * (global_recon/models/global_recon_model.py:428-570), the residual registry global_recon/models/loss_func.py:314-340
  * and torch.optim.Adam.step (:563,:642).

@@ -142,6 +142,38 @@ def smpl_vectors(assets):
     }
 
 
+def nets_vectors():
+    """MotionTrajJointModel.inference of the reference with the seeded stand-in weights of
+    glamr_b200.synthetic_nets loaded into its modules, latents injected (CPU and CUDA generators differ)."""
+    from motion_infiller.models.motion_traj_joint_model import MotionTrajJointModel
+    from motion_infiller.utils.config_motion_traj import Config as MTConfig
+    from glamr_b200.synthetic_nets import make_prior_states
+    mt = MotionTrajJointModel(MTConfig('joint_motion_traj_demo'), torch.device('cpu'), None)
+    st_m, st_t = make_prior_states(1234)
+    for mod, st in [(mt.mfiller, st_m), (mt.traj_predictor, st_t)]:
+        own = mod.state_dict()
+        assert all(k in own and tuple(own[k].shape) == v.shape for k, v in st.items()), 'state-dict names/shapes differ from the reference'
+        res = mod.load_state_dict({k: torch.tensor(v) for k, v in st.items()}, strict=False)
+        assert not res.unexpected_keys
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    for tag, B, T in [('b3_t75', 3, 75), ('b1_t300', 1, 300), ('b2_t40', 2, 40)]:
+        pose = torch.randn(B, T, 69, generator=g) * 0.3
+        mask = torch.ones(B, T)
+        mask[0, 20:45] = 0
+        if B > 1:
+            mask[1, T - 12:T - 2] = 0
+        nwin = int(np.ceil((T - 10) / 30))
+        batch = {'in_body_pose': pose * mask[..., None], 'frame_mask': mask, 'in_motion_latent': torch.randn(nwin, 128, generator=g),
+                 'in_traj_latent': torch.randn(1, 128, generator=g)}
+        res = mt.inference({k: v.clone() for k, v in batch.items()}, sample_num=1)
+        for k, v in batch.items():
+            out[f'{tag}/in/{k}'] = v.numpy()
+        for k in ['infer_out_body_pose', 'infer_out_local_traj_tp', 'infer_out_orient', 'infer_out_trans', 'infer_out_pose']:
+            out[f'{tag}/{k}'] = res[k].detach().numpy()
+    return out
+
+
 def globalopt_case(assets, name, cfg_id, P, T, gaps, niters):
     in_dict = make_in_dict(assets, P, T, seed=0, gaps=gaps, seq_name=name)
     model, cfg = ref_env.make_reference_optimizer(cfg_id, niters=niters)
@@ -211,11 +243,15 @@ def globalopt_case(assets, name, cfg_id, P, T, gaps, niters):
     return rec
 
 
-def main():
+def main(only=None):
+    if only == 'nets':
+        np.savez_compressed(os.path.join(HERE, 'nets.npz'), **nets_vectors())
+        return
     assets = make_smpl_assets(0)
     np.savez_compressed(os.path.join(HERE, 'rotations.npz'), **rotation_vectors())
     np.savez_compressed(os.path.join(HERE, 'traj_codec.npz'), **traj_vectors())
     np.savez_compressed(os.path.join(HERE, 'smpl.npz'), **smpl_vectors(assets))
+    np.savez_compressed(os.path.join(HERE, 'nets.npz'), **nets_vectors())
     for case in GLOBALOPT_CASES:
         rec = globalopt_case(assets, *case)
         np.savez_compressed(os.path.join(HERE, f'globalopt_{case[0]}.npz'), **rec)
@@ -223,4 +259,4 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

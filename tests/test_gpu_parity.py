@@ -267,3 +267,68 @@ def test_product_fails_loudly_on_cpu_device(smpl_assets):
     gold, cfg, in_dict = case_setup('static_p1_t24', smpl_assets)
     with pytest.raises(GlamrError):
         GlobalReconOptimizer(cfg, torch.device('cpu'), None, smpl=smpl_assets, mt_model=ReplayMT(gold))
+
+
+# ------------------------------------------------------------------------------------------------ learned prior
+@pytest.fixture(scope='module')
+def cuda_prior(smpl_assets):
+    from glamr_b200.motion_traj import MotionTrajJointModel
+    from glamr_b200.smpl import SMPL
+    from glamr_b200.synthetic_nets import make_prior_states
+    return MotionTrajJointModel(None, torch.device(DEV), None, smpl=SMPL(smpl_assets, device=DEV), states=make_prior_states(1234))
+
+
+@pytest.mark.parametrize('tag', ['b3_t75', 'b1_t300', 'b2_t40'])
+def test_prior_inference_matches_reference_golden(tag, cuda_prior):
+    """infiller (transformer, 50-frame autoregressive windows, key-padding masks, ragged last window) + trajectory
+    predictor (MLP + bi-LSTM) vs the executed reference networks with identical weights and injected latents"""
+    g = load_golden('nets')
+    batch = {k: _cuda(g[f'{tag}/in/{k}']) for k in ['in_body_pose', 'frame_mask', 'in_motion_latent', 'in_traj_latent']}
+    out = cuda_prior.inference(batch, sample_num=1)
+    for k, tol in [('infer_out_body_pose', 1e-4), ('infer_out_local_traj_tp', 1e-4), ('infer_out_orient', 5e-4), ('infer_out_trans', 5e-4),
+                   ('infer_out_pose', 5e-4)]:
+        got = out[k].cpu().numpy()
+        assert got.shape == g[f'{tag}/{k}'].shape, (k, got.shape, g[f'{tag}/{k}'].shape)
+        np.testing.assert_allclose(got, g[f'{tag}/{k}'], atol=tol, err_msg=f'{tag} {k}')
+
+
+def test_prior_batch_consistency(cuda_prior):
+    """a sequence gives the same result alone and inside a batch of 64 (BASELINE config 3 shape: 64 x 120)"""
+    gen = torch.Generator().manual_seed(3)
+    pose = (torch.randn(64, 120, 69, generator=gen) * 0.3).to(DEV)
+    mask = torch.ones(64, 120, device=DEV)
+    mask[:, 40:70] = 0
+    lat = {'in_motion_latent': torch.randn(4, 128, generator=gen).to(DEV), 'in_traj_latent': torch.randn(1, 128, generator=gen).to(DEV)}
+    full = cuda_prior.inference({'in_body_pose': pose * mask[..., None], 'frame_mask': mask, **lat})
+    one = cuda_prior.inference({'in_body_pose': (pose * mask[..., None])[5:6], 'frame_mask': mask[5:6], **lat})
+    assert (full['infer_out_body_pose'][5] - one['infer_out_body_pose'][0]).abs().max() < 1e-5
+    assert (full['infer_out_local_traj_tp'][:, 5] - one['infer_out_local_traj_tp'][:, 0]).abs().max() < 1e-5
+    assert full['infer_out_body_pose'].shape == (64, 1, 120, 69) and full['infer_out_local_traj_tp'].shape == (120, 64, 1, 11)
+
+
+def test_full_pipeline_with_cuda_prior_matches_oracle(smpl_assets, cuda_prior):
+    """init_data (infill -> trajectory) + optimisation, CUDA end to end vs the oracle end to end, same weights/latents"""
+    from glamr_b200.config import Config
+    from glamr_b200.recon import GlobalReconOptimizer
+    from glamr_b200.synthetic import make_in_dict
+    from glamr_b200.synthetic_nets import make_prior_states
+    from helpers import LatentInjector
+    from oracle.global_opt import OracleGlobalRecon
+    from oracle.nets import MotionTrajJoint
+    from oracle.smpl import OracleSMPL
+    cfg = Config('glamr_dynamic')
+    for st in cfg.opt_stage_specs.values():
+        st['opt_niters'] = 5
+    in_dict = make_in_dict(smpl_assets, 1, 70, seed=3, gaps=True)
+    model = GlobalReconOptimizer(cfg, torch.device(DEV), None, smpl=cuda_prior.smpl, mt_model=LatentInjector(cuda_prior, 9))
+    out = model.optimize(copy.deepcopy(in_dict))
+    st_m, st_t = make_prior_states(1234)
+    ora = OracleGlobalRecon(copy.deepcopy(cfg), smpl_assets, mt_model=LatentInjector(MotionTrajJoint(st_m, st_t, OracleSMPL(smpl_assets)), 9))
+    ref = ora.optimize(copy.deepcopy(in_dict))
+    pd, pr = out['person_data'][0], ref['person_data'][0]
+    np.testing.assert_allclose(pd['smpl_pose'], pr['smpl_pose'], atol=2e-4, err_msg='infilled body pose')
+    np.testing.assert_allclose(pd['traj_local_pred'], pr['traj_local_pred'], atol=2e-4)
+    vis = pr['vis_frames']
+    np.testing.assert_allclose(pd['smpl_orient_world'][vis], pr['smpl_orient_world'][vis], atol=3e-3)
+    np.testing.assert_allclose(pd['root_trans_world'][vis], pr['root_trans_world'][vis], atol=3e-3)
+    np.testing.assert_allclose(out['cam_pose'], ref['cam_pose'], atol=3e-3)
