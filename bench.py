@@ -105,11 +105,15 @@ def make_problem(args, persons):
 def cpu_port_timing(assets, in_dict, cfg, iters, warm=3):
     """the oracle port (torch CPU, all host threads) on the same workload: seconds per iteration"""
     import torch
-    from glamr_b200.synthetic import SyntheticPrior
+    from glamr_b200.synthetic import LatentInjector
+    from glamr_b200.synthetic_nets import make_prior_states
     from oracle.global_opt import OracleGlobalRecon
+    from oracle.nets import MotionTrajJoint
+    from oracle.smpl import OracleSMPL
     cfg = copy.deepcopy(cfg)
     stage, specs = next(iter(cfg.opt_stage_specs.items()))
-    model = OracleGlobalRecon(cfg, assets, mt_model=SyntheticPrior(0))
+    st_m, st_t = make_prior_states(1234)
+    model = OracleGlobalRecon(cfg, assets, mt_model=LatentInjector(MotionTrajJoint(st_m, st_t, OracleSMPL(assets)), 0))
     data = model.init_data(copy.deepcopy(in_dict))
     times = []
     model.optimize_main(data, specs['opt_variables'], specs['opt_lr'], warm + iters, specs['loss_cfg'], {'stage': stage},
@@ -159,7 +163,9 @@ def run_ours(args):
     from glamr_b200 import lib as L
     from glamr_b200.recon import GlobalReconOptimizer
     from glamr_b200.smpl import SMPL
-    from glamr_b200.synthetic import SyntheticPrior
+    from glamr_b200.motion_traj import MotionTrajJointModel
+    from glamr_b200.synthetic import LatentInjector
+    from glamr_b200.synthetic_nets import make_prior_states
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -172,11 +178,12 @@ def run_ours(args):
     stage, specs = next(iter(cfg.opt_stage_specs.items()))
     K, W = args.steps, max(args.warmup, 3)
     smpl = SMPL(assets, device=dev)
+    prior = MotionTrajJointModel(None, dev, None, smpl=smpl, states=make_prior_states(1234))
 
     def new_model(graph=True):
         c = copy.deepcopy(cfg)
         c.grecon_model_specs['use_cuda_graph'] = graph
-        return GlobalReconOptimizer(c, dev, None, smpl=smpl, mt_model=SyntheticPrior(0, dev), dist=(rank, world) if world > 1 else None)
+        return GlobalReconOptimizer(c, dev, None, smpl=smpl, mt_model=LatentInjector(prior, 0), dist=(rank, world) if world > 1 else None)
 
     # ---------------- device-resident timing: K iterations, L2 flushed between iterations, CUDA events per iteration
     model = new_model()
@@ -286,7 +293,7 @@ def run_ours(args):
             'config': {'workload': f'{CFG_ID}:init_opt, {persons} person(s) x {args.frames} frames, full-LBS every iteration',
                        'persons': persons, 'frames': args.frames, 'parallelism': f'persons sharded over {world} GPU(s), 1 allreduce/iter' if world > 1 else 'single GPU',
                        'l2': 'flushed between timed iterations (256 MiB fill); value_l2_warm = back-to-back replays',
-                       'cuda_graph': graph is not None, 'lbs_mode': args.lbs_mode, 'prior': 'SyntheticPrior (seeded stand-in for the learned prior outputs)'},
+                       'cuda_graph': graph is not None, 'lbs_mode': args.lbs_mode, 'prior': 'CUDA infiller+traj-pred with seeded stand-in weights (no checkpoints offline), latents injected'},
             'clocks': clocks,
             'gpu_launches': 12 * K,
             'e2e': {'value': units * K / e2e_s, 'unit': 'frame*person*iter/s', 'h2d_bytes_per_step': h2d / K, 'd2h_bytes_per_step': d2h / K,

@@ -172,3 +172,22 @@ class SyntheticPrior:
                 'infer_out_local_traj_tp': t(local).reshape(T, B, 1, 11),
                 'infer_out_orient': torch.zeros((B, 1, T, 3), dtype=torch.float32, device=self.device),
                 'infer_out_trans': torch.zeros((B, 1, T, 3), dtype=torch.float32, device=self.device)}
+
+
+class LatentInjector:
+    """Wraps a MotionTrajJointModel-like object and injects seeded latents through the reference's own injection
+    points (`in_motion_latent`, `in_traj_latent`) so CPU and CUDA runs sample the same z."""
+
+    def __init__(self, model, seed=0):
+        self.model, self.seed, self.calls = model, seed, 0
+
+    def inference(self, batch, sample_num=1):
+        import torch
+        T = batch['in_body_pose'].shape[1]
+        g = torch.Generator().manual_seed(self.seed + 101 * self.calls)
+        self.calls += 1
+        b = dict(batch)
+        dev = batch['in_body_pose'].device
+        b['in_motion_latent'] = torch.randn(int(np.ceil((T - 10) / 30)), 128, generator=g).to(dev)
+        b['in_traj_latent'] = torch.randn(1, 128, generator=g).to(dev)
+        return self.model.inference(b, sample_num=sample_num)

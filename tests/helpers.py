@@ -40,20 +40,4 @@ def case_setup(name, smpl_assets):
     return gold, cfg, in_dict
 
 
-class LatentInjector:
-    """Wraps a MotionTrajJointModel-like object and injects seeded latents through the reference's own injection
-    points (`in_motion_latent`, `in_traj_latent`) so CPU and CUDA runs sample the same z."""
-
-    def __init__(self, model, seed=0):
-        self.model, self.seed, self.calls = model, seed, 0
-
-    def inference(self, batch, sample_num=1):
-        T = batch['in_body_pose'].shape[1]
-        g = torch.Generator().manual_seed(self.seed + 101 * self.calls)
-        self.calls += 1
-        b = dict(batch)
-        nwin = int(np.ceil((T - 10) / 30))
-        dev = batch['in_body_pose'].device
-        b['in_motion_latent'] = torch.randn(nwin, 128, generator=g).to(dev)
-        b['in_traj_latent'] = torch.randn(1, 128, generator=g).to(dev)
-        return self.model.inference(b, sample_num=sample_num)
+from glamr_b200.synthetic import LatentInjector  # noqa: E402,F401  (re-exported for the tests)
