@@ -4,7 +4,7 @@
 
 namespace glamr {
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 512;
 
 // Inclusive scan (forward or reverse) of `count` floats at data[k * stride], in place, by one CTA of kScanThreads.
 __device__ __forceinline__ void block_scan_inplace(float* data, int count, int stride, bool reverse, float* smem /*[kScanThreads/32 + 1]*/) {
@@ -25,7 +25,7 @@ __device__ __forceinline__ void block_scan_inplace(float* data, int count, int s
     if (wid == 0) {
       float w = (lane < NW) ? smem[lane] : 0.0f;
 #pragma unroll
-      for (int o = 1; o < NW; o <<= 1) {
+      for (int o = 1; o < 32; o <<= 1) {
         const float u = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += u;
       }

@@ -267,36 +267,30 @@ GLAMR_HD void rotmat_to_quat(const float* m, float* q) {
     q[0] = (m[3] - m[1]) / sq; q[1] = (m[2] + m[6]) / sq; q[2] = (m[5] + m[7]) / sq; q[3] = 0.25f * sq;
   }
 }
+// One branch of the VJP with compile-time indices (keeps everything in registers): D = 1 + sd0 m[d0] + sd1 m[d1] + sd2 m[d2]
+// (trace branch: all +), slot IS holds 0.25*sq, slots IA/IB/IC hold (m[P] + S m[N]) / sq.
+template <int IS, int IA, int PA, int NA, int SA, int IB, int PB, int NB, int SB, int IC, int PC, int NC, int SC, int D0, int D1, int D2, int S1, int S2>
+GLAMR_HD void rotmat_to_quat_vjp_branch(const float* m, const float* gq, float* gm) {
+  const float D = 1.0f + m[D0] + (float)S1 * m[D1] + (float)S2 * m[D2];
+  const float Dc = fmaxf(D, kEps6);
+  const float rs = sqrtf(Dc);
+  const float sq = rs * 2.0f, isq = 1.0f / sq;
+  const float na = m[PA] + (float)SA * m[NA], nb = m[PB] + (float)SB * m[NB], nc = m[PC] + (float)SC * m[NC];
+  const float gsq = 0.25f * gq[IS] - (gq[IA] * na + gq[IB] * nb + gq[IC] * nc) * isq * isq;
+  gm[PA] += gq[IA] * isq; gm[NA] += (float)SA * gq[IA] * isq;
+  gm[PB] += gq[IB] * isq; gm[NB] += (float)SB * gq[IB] * isq;
+  gm[PC] += gq[IC] * isq; gm[NC] += (float)SC * gq[IC] * isq;
+  const float gD = (D >= kEps6) ? gsq / rs : 0.0f;   // d(2 sqrt D)/dD = 1/sqrt(D); clamp_min passes the gradient when D >= eps
+  gm[D0] += gD; gm[D1] += (float)S1 * gD; gm[D2] += (float)S2 * gD;
+}
 GLAMR_HD void rotmat_to_quat_vjp(const float* m, const float* gq, float* gm) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) gm[i] = 0.0f;
   const int br = rotmat_quat_branch(m);
-  // per branch: D (under the sqrt), the index of the 0.25*sq component, three (num, sign pattern) pairs
-  float D;
-  int is;             // quaternion slot holding 0.25*sq
-  int ia[3];          // slots of the three divided components
-  int p[3], n[3];     // numerator = m[p] + sgn * m[n]
-  float sgn[3];
-  if (br == 0) { D = m[0] + m[4] + m[8] + 1.0f; is = 0; ia[0] = 1; p[0] = 7; n[0] = 5; sgn[0] = -1; ia[1] = 2; p[1] = 2; n[1] = 6; sgn[1] = -1; ia[2] = 3; p[2] = 3; n[2] = 1; sgn[2] = -1; }
-  else if (br == 1) { D = 1.0f + m[0] - m[4] - m[8]; is = 1; ia[0] = 0; p[0] = 7; n[0] = 5; sgn[0] = -1; ia[1] = 2; p[1] = 1; n[1] = 3; sgn[1] = 1; ia[2] = 3; p[2] = 2; n[2] = 6; sgn[2] = 1; }
-  else if (br == 2) { D = 1.0f + m[4] - m[0] - m[8]; is = 2; ia[0] = 0; p[0] = 2; n[0] = 6; sgn[0] = -1; ia[1] = 1; p[1] = 1; n[1] = 3; sgn[1] = 1; ia[2] = 3; p[2] = 5; n[2] = 7; sgn[2] = 1; }
-  else { D = 1.0f + m[8] - m[0] - m[4]; is = 3; ia[0] = 0; p[0] = 3; n[0] = 1; sgn[0] = -1; ia[1] = 1; p[1] = 2; n[1] = 6; sgn[1] = 1; ia[2] = 2; p[2] = 5; n[2] = 7; sgn[2] = 1; }
-  const float Dc = fmaxf(D, kEps6);
-  const float sq = sqrtf(Dc) * 2.0f;
-  float gsq = 0.25f * gq[is];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float num = m[p[k]] + sgn[k] * m[n[k]];
-    const float g = gq[ia[k]];
-    gsq -= g * num / (sq * sq);
-    gm[p[k]] += g / sq;
-    gm[n[k]] += sgn[k] * g / sq;
-  }
-  const float gD = (D >= kEps6) ? gsq / sqrtf(Dc) : 0.0f;   // d(2 sqrt D)/dD = 1/sqrt(D); clamp passes grad when D >= eps
-  if (br == 0) { gm[0] += gD; gm[4] += gD; gm[8] += gD; }
-  else if (br == 1) { gm[0] += gD; gm[4] -= gD; gm[8] -= gD; }
-  else if (br == 2) { gm[4] += gD; gm[0] -= gD; gm[8] -= gD; }
-  else { gm[8] += gD; gm[0] -= gD; gm[4] -= gD; }
+  if (br == 0) rotmat_to_quat_vjp_branch<0, 1, 7, 5, -1, 2, 2, 6, -1, 3, 3, 1, -1, 0, 4, 8, 1, 1>(m, gq, gm);
+  else if (br == 1) rotmat_to_quat_vjp_branch<1, 0, 7, 5, -1, 2, 1, 3, 1, 3, 2, 6, 1, 0, 4, 8, -1, -1>(m, gq, gm);
+  else if (br == 2) rotmat_to_quat_vjp_branch<2, 0, 2, 6, -1, 1, 1, 3, 1, 3, 5, 7, 1, 4, 0, 8, -1, -1>(m, gq, gm);
+  else rotmat_to_quat_vjp_branch<3, 0, 3, 1, -1, 1, 2, 6, 1, 2, 5, 7, 1, 8, 0, 4, -1, -1>(m, gq, gm);
 }
 
 // ------------------------------------------------------------------------------------------------ q <-> axis-angle

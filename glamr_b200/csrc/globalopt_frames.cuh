@@ -259,68 +259,83 @@ GLAMR_HD void cam_forward(const OptCtx& c, int t) {
 // Writes kp_pred, orient_ciw, trans_ciw, g_orient, g_trans, g_cam and adds un-normalised sums to `acc`.
 // The SMPL dependence is handled through the rigid form  joints = R(orient) b_k + trans  (b_k body-frame offsets,
 // constant w.r.t. the optimisation variables): dL/dR = sum_k g_k (R^T (joint_k - trans))^T.
-GLAMR_HD void frame_residuals(const OptCtx& c, int p, int t, TermAcc& acc) {
+// Contribution of joint k of frame-person (p,t) to the reprojection terms (loss_func.py:15-57, geometry.py:23-25) and to
+// the gradients w.r.t. camera (g_Rc, g_tc), translation (g_tw) and the SMPL root rotation matrix (g_Rs).  The CUDA kernel
+// runs one lane per joint and sums these with warp shuffles; the host harness loops over k.
+struct KpGrad {
+  float g_tc[3], g_Rc[9], g_tw[3], g_Rs[9];
+  double kp, dist;
+  GLAMR_HD void clear() {
+    for (int i = 0; i < 3; ++i) { g_tc[i] = 0.0f; g_tw[i] = 0.0f; }
+    for (int i = 0; i < 9; ++i) { g_Rc[i] = 0.0f; g_Rs[i] = 0.0f; }
+    kp = 0.0; dist = 0.0;
+  }
+};
+GLAMR_HD void kp_joint_terms(const OptCtx& c, int p, int t, int k, const float* jw, const float* Rc, const float* tc, const float* Rs,
+                             const float* tw, KpGrad& o) {
+  const glamr_person_t& ps = c.pb.persons[p];
+  const int J = c.pb.J;
+  const size_t n = (size_t)p * c.pb.T + t;
+  const float* K = ps.cam_K + (size_t)t * 9;
+  const float gsk = c.gs[GLAMR_T_KP_2D];
+  float Xc[3], uv[2];
+  mat3_vec(Rc, jw, Xc);
+  Xc[0] += tc[0]; Xc[1] += tc[1]; Xc[2] += tc[2];
+  project(K, Xc, uv);
+  c.sc.kp_pred[(n * J + k) * 2] = uv[0];
+  c.sc.kp_pred[(n * J + k) * 2 + 1] = uv[1];
+  const float dx = uv[0] - ps.kp_target[((size_t)t * J + k) * 2];
+  const float dy = uv[1] - ps.kp_target[((size_t)t * J + k) * 2 + 1];
+  const float wk = ps.kp_w[(size_t)t * J + k];
+  const float dm = ps.kp_dist_mask[(size_t)t * J + k];
+  if (dm != 0.0f) o.dist += (double)(dm * sqrtf(dx * dx + dy * dy));
+  if (wk != 0.0f) {
+    o.kp += (double)wk * ((double)gmof(dx) + (double)gmof(dy));
+    if (gsk != 0.0f) {
+      const float guv[2] = {gsk * wk * gmof_grad(dx), gsk * wk * gmof_grad(dy)};
+      float gX[3], gj[3], b[3], d[3];
+      project_vjp(K, Xc, guv, gX);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        o.g_tc[a] += gX[a];
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) o.g_Rc[a * 3 + bb] += gX[a] * jw[bb];
+      }
+      mat3_tvec(Rc, gX, gj);
+      d[0] = jw[0] - tw[0]; d[1] = jw[1] - tw[1]; d[2] = jw[2] - tw[2];
+      mat3_tvec(Rs, d, b);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        o.g_tw[a] += gj[a];
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) o.g_Rs[a * 3 + bb] += gj[a] * b[bb];
+      }
+    }
+  }
+}
+
+// Everything of frame-person (p,t) that is not per joint, given the summed joint contributions `kg`.
+GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAcc& acc) {
   const glamr_problem_t& pb = c.pb;
   const glamr_person_t& ps = pb.persons[p];
-  const int T = pb.T, J = pb.J;
+  const int T = pb.T;
   const size_t n = (size_t)p * T + t;
   const float* ow = c.sc.orient_world + n * 3;
   const float* tw = c.sc.trans_world + n * 3;
   float Rc[9], tc[3];
   mat34_R(c.sc.cam + (size_t)t * 12, Rc);
   tc[0] = c.sc.cam[(size_t)t * 12 + 3]; tc[1] = c.sc.cam[(size_t)t * 12 + 7]; tc[2] = c.sc.cam[(size_t)t * 12 + 11];
-  float g_ow[3] = {0, 0, 0}, g_tw[3] = {0, 0, 0}, g_Rc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, g_tc[3] = {0, 0, 0};
-
-  // ---- 2D reprojection (loss_func.py:15-57, geometry.py:23-25)
-  {
-    float Rs[9], g_Rs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    rodrigues_smplx(ow, Rs);
-    const float* K = ps.cam_K + (size_t)t * 9;
-    const float gsk = c.gs[GLAMR_T_KP_2D];
-    bool any = false;
-    for (int k = 0; k < J; ++k) {
-      const float* jw = c.sc.joints_world + (n * J + k) * 3;
-      float Xc[3], uv[2];
-      mat3_vec(Rc, jw, Xc);
-      Xc[0] += tc[0]; Xc[1] += tc[1]; Xc[2] += tc[2];
-      project(K, Xc, uv);
-      c.sc.kp_pred[(n * J + k) * 2] = uv[0];
-      c.sc.kp_pred[(n * J + k) * 2 + 1] = uv[1];
-      const float dx = uv[0] - ps.kp_target[((size_t)t * J + k) * 2];
-      const float dy = uv[1] - ps.kp_target[((size_t)t * J + k) * 2 + 1];
-      const float wk = ps.kp_w[(size_t)t * J + k];
-      const float dm = ps.kp_dist_mask[(size_t)t * J + k];
-      if (dm != 0.0f) acc.v[GLAMR_T_KP_2D_DIST] += (double)(dm * sqrtf(dx * dx + dy * dy));
-      if (wk != 0.0f) {
-        acc.v[GLAMR_T_KP_2D] += (double)wk * ((double)gmof(dx) + (double)gmof(dy));
-        if (gsk != 0.0f) {
-          any = true;
-          const float guv[2] = {gsk * wk * gmof_grad(dx), gsk * wk * gmof_grad(dy)};
-          float gX[3], gj[3], b[3], d[3];
-          project_vjp(K, Xc, guv, gX);
+  float g_ow[3] = {0, 0, 0}, g_tw[3], g_Rc[9], g_tc[3];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            g_tc[a] += gX[a];
+  for (int k = 0; k < 3; ++k) { g_tw[k] = kg.g_tw[k]; g_tc[k] = kg.g_tc[k]; }
 #pragma unroll
-            for (int bb = 0; bb < 3; ++bb) g_Rc[a * 3 + bb] += gX[a] * jw[bb];
-          }
-          mat3_tvec(Rc, gX, gj);
-          d[0] = jw[0] - tw[0]; d[1] = jw[1] - tw[1]; d[2] = jw[2] - tw[2];
-          mat3_tvec(Rs, d, b);
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            g_tw[a] += gj[a];
-#pragma unroll
-            for (int bb = 0; bb < 3; ++bb) g_Rs[a * 3 + bb] += gj[a] * b[bb];
-          }
-        }
-      }
-    }
-    if (any) {
-      float g[3];
-      rodrigues_smplx_vjp(ow, g_Rs, g);
-      g_ow[0] += g[0]; g_ow[1] += g[1]; g_ow[2] += g[2];
-    }
+  for (int k = 0; k < 9; ++k) g_Rc[k] = kg.g_Rc[k];
+  acc.v[GLAMR_T_KP_2D] += kg.kp;
+  acc.v[GLAMR_T_KP_2D_DIST] += kg.dist;
+  if (c.gs[GLAMR_T_KP_2D] != 0.0f) {
+    float g[3];
+    rodrigues_smplx_vjp(ow, kg.g_Rs, g);
+    g_ow[0] += g[0]; g_ow[1] += g[1]; g_ow[2] += g[2];
   }
 
   // ---- camera-frame pose of the person + cam_traj_rot / cam_traj_trans (global_recon_model.py:512-513, loss_func.py:147-186)
@@ -508,6 +523,20 @@ GLAMR_HD void frame_residuals(const OptCtx& c, int p, int t, TermAcc& acc) {
   for (int k = 0; k < 9; ++k) c.sc.g_cam[n * 12 + k] = g_Rc[k];
 #pragma unroll
   for (int k = 0; k < 3; ++k) c.sc.g_cam[n * 12 + 9 + k] = g_tc[k];
+}
+
+// Sequential form (host harness): all joints of (p,t), then the rest.
+GLAMR_HD void frame_residuals(const OptCtx& c, int p, int t, TermAcc& acc) {
+  const size_t n = (size_t)p * c.pb.T + t;
+  float Rc[9], tc[3], Rs[9];
+  mat34_R(c.sc.cam + (size_t)t * 12, Rc);
+  tc[0] = c.sc.cam[(size_t)t * 12 + 3]; tc[1] = c.sc.cam[(size_t)t * 12 + 7]; tc[2] = c.sc.cam[(size_t)t * 12 + 11];
+  rodrigues_smplx(c.sc.orient_world + n * 3, Rs);
+  KpGrad kg;
+  kg.clear();
+  for (int k = 0; k < c.pb.J; ++k)
+    kp_joint_terms(c, p, t, k, c.sc.joints_world + (n * c.pb.J + k) * 3, Rc, tc, Rs, c.sc.trans_world + n * 3, kg);
+  frame_rest(c, p, t, kg, acc);
 }
 
 // ------------------------------------------------------------------------------------------------ camera backward

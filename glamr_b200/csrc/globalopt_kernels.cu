@@ -35,8 +35,29 @@ __device__ void block_reduce_terms(const TermAcc& acc, double* out /*[NUM_TERMS]
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(kScanThreads) traj_forward_kernel(OptCtx c) {
+// last-block-done ticket: returns true in exactly one CTA of the grid, after all CTAs passed this point
+__device__ bool grid_last_block(unsigned int* ticket) {
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(ticket, 1u);
+    last = (old == gridDim.x - 1);
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (last) __threadfence();
+  return last;
+}
+
+// blocks [0,P): trajectory codec of one person; blocks [P, P+cam_blocks): camera of 256 frames each (modes 0-2)
+__global__ void __launch_bounds__(kScanThreads) traj_cam_forward_kernel(OptCtx c, int with_cam) {
   __shared__ float sm[kScanThreads / 32 + 1];
+  if ((int)blockIdx.x >= c.pb.P) {
+    const int t = (blockIdx.x - c.pb.P) * kScanThreads + threadIdx.x;
+    if (with_cam && t < c.pb.T) cam_forward(c, t);
+    return;
+  }
   const int p = blockIdx.x;
   const glamr_person_t& ps = c.pb.persons[p];
   const int len = ps.len, T = c.pb.T;
@@ -58,22 +79,58 @@ __global__ void __launch_bounds__(kFrameThreads) cam_forward_kernel(OptCtx c) {
   if (t < c.pb.T) cam_forward(c, t);
 }
 
-__global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c, double* partial) {
+// One warp per frame-person: lanes = joints for the SMPL joint assembly (lib/models/smpl.py:299-315, fused here) and the
+// reprojection terms, warp-shuffle sums, then lane 0 finishes the per-frame terms.  4 frame-persons per CTA.
+__global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c, SmplDev m, SmplWorkspace wo, int n_begin, double* partial) {
   __shared__ double sm[(kFrameThreads / 32) * GLAMR_NUM_TERMS];
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int N = c.pb.P * c.pb.T;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = blockIdx.x * (kFrameThreads / 32) + wid;
+  const int N = c.pb.P * c.pb.T, J = c.pb.J;
   TermAcc acc;
   acc.clear();
   if (n < N) {
     const int p = n / c.pb.T, t = n - p * c.pb.T;
     if (p >= c.pb.p_begin && p < c.pb.p_end) {
-      frame_residuals(c, p, t, acc);
-    } else {
+      const int nl = n - n_begin;
+      const float* tw = c.sc.trans_world + (size_t)n * 3;
+      const float sc = c.pb.scale_all ? c.pb.scale_all[n] : 1.0f;
+      float root[3], Rc[9], tc[3], Rs[9];
+      raw_joint(m, wo, nl, m.joint_map[0], root);
+      mat34_R(c.sc.cam + (size_t)t * 12, Rc);
+      tc[0] = c.sc.cam[(size_t)t * 12 + 3]; tc[1] = c.sc.cam[(size_t)t * 12 + 7]; tc[2] = c.sc.cam[(size_t)t * 12 + 11];
+      rodrigues_smplx(c.sc.orient_world + (size_t)n * 3, Rs);
+      KpGrad kg;
+      kg.clear();
+      for (int k = lane; k < J; k += 32) {
+        float v[3], jw[3];
+        raw_joint(m, wo, nl, m.joint_map[k], v);
+        jw[0] = (v[0] - root[0]) * sc + tw[0];
+        jw[1] = (v[1] - root[1]) * sc + tw[1];
+        jw[2] = (v[2] - root[2]) * sc + tw[2];
+        float* o = c.sc.joints_world + ((size_t)n * J + k) * 3;
+        o[0] = jw[0]; o[1] = jw[1]; o[2] = jw[2];
+        kp_joint_terms(c, p, t, k, jw, Rc, tc, Rs, tw, kg);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { kg.g_tc[k] = warp_sum(kg.g_tc[k]); kg.g_tw[k] = warp_sum(kg.g_tw[k]); }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { kg.g_Rc[k] = warp_sum(kg.g_Rc[k]); kg.g_Rs[k] = warp_sum(kg.g_Rs[k]); }
+      kg.kp = warp_sum(kg.kp);
+      kg.dist = warp_sum(kg.dist);
+      if (lane == 0) frame_rest(c, p, t, kg, acc);
+    } else if (lane == 0) {
       for (int k = 0; k < 3; ++k) { c.sc.g_orient[(size_t)n * 3 + k] = 0.0f; c.sc.g_trans[(size_t)n * 3 + k] = 0.0f; }
       for (int k = 0; k < 12; ++k) c.sc.g_cam[(size_t)n * 12 + k] = 0.0f;
     }
   }
-  block_reduce_terms(acc, partial + (size_t)blockIdx.x * GLAMR_NUM_TERMS, sm);
+  if (lane == 0)
+    for (int k = 0; k < GLAMR_NUM_TERMS; ++k) sm[wid * GLAMR_NUM_TERMS + k] = acc.v[k];
+  __syncthreads();
+  if (threadIdx.x < GLAMR_NUM_TERMS) {
+    double s = 0.0;
+    for (int w = 0; w < kFrameThreads / 32; ++w) s += sm[w * GLAMR_NUM_TERMS + threadIdx.x];
+    partial[(size_t)blockIdx.x * GLAMR_NUM_TERMS + threadIdx.x] = s;
+  }
 }
 
 __global__ void __launch_bounds__(kFrameThreads) camera_backward_kernel(OptCtx c, double* partial) {
@@ -90,31 +147,8 @@ __global__ void __launch_bounds__(kFrameThreads) camera_scatter_kernel(OptCtx c)
   if (s < c.pb.T) camera_scatter_to_persons(c, s);
 }
 
-__global__ void __launch_bounds__(kScanThreads) traj_backward_kernel(OptCtx c, double* partial) {
-  __shared__ float sm[kScanThreads / 32 + 1];
-  __shared__ double smd[(kScanThreads / 32) * GLAMR_NUM_TERMS];
-  const int p = blockIdx.x;
-  const glamr_person_t& ps = c.pb.persons[p];
-  const int len = ps.len, T = c.pb.T;
-  const size_t n0 = (size_t)p * T + ps.start;
-  TermAcc acc;
-  acc.clear();
-  for (int t = threadIdx.x; t < T; t += kScanThreads) traj_back_pre(c, p, t, acc);
-  __syncthreads();
-  block_scan_inplace(c.sc.g_xy + 2 * n0, len, 2, true, sm);
-  block_scan_inplace(c.sc.g_xy + 2 * n0 + 1, len, 2, true, sm);
-  __syncthreads();
-  for (int i = threadIdx.x; i < len; i += kScanThreads) traj_back_mid(c, p, i, acc);
-  __syncthreads();
-  block_scan_inplace(c.sc.g_head + n0, len, 1, true, sm);
-  __syncthreads();
-  for (int i = threadIdx.x; i < len; i += kScanThreads) traj_back_post(c, p, i, acc);
-  block_reduce_terms(acc, partial + (size_t)blockIdx.x * GLAMR_NUM_TERMS, smd);
-}
-
 // loss partials -> un-normalised term sums (reduce_buf tail); fixed camera: sum the per-frame gradients over T
-__global__ void __launch_bounds__(256) reduce_kernel(OptCtx c, const double* partial, int n_slots, float* reduce_buf) {
-  __shared__ double sm[8 * 16];
+__device__ void reduce_tail(const OptCtx& c, const double* partial, int n_slots, float* reduce_buf, double* sm /*[8*16]*/) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid < GLAMR_NUM_TERMS) {
     double s = 0.0;
@@ -140,36 +174,67 @@ __global__ void __launch_bounds__(256) reduce_kernel(OptCtx c, const double* par
   }
 }
 
+// blocks [0,P): reverse trajectory codec of one person; blocks [P, P+cam_blocks): camera backward of 256 frames (modes
+// 0-2; mode 3 runs camera_backward/scatter kernels first).  The last CTA to finish folds all partial sums.
+__global__ void __launch_bounds__(kScanThreads) traj_cam_backward_kernel(OptCtx c, int with_cam, double* partial_traj, const double* partial_all,
+                                                                         int n_slots, float* reduce_buf, unsigned int* ticket) {
+  __shared__ float sm[kScanThreads / 32 + 1];
+  __shared__ double smd[(kScanThreads / 32) * GLAMR_NUM_TERMS];
+  TermAcc acc;
+  acc.clear();
+  if ((int)blockIdx.x >= c.pb.P) {
+    const int t = (blockIdx.x - c.pb.P) * kScanThreads + threadIdx.x;
+    if (with_cam && t < c.pb.T) camera_backward(c, t, acc);
+  } else {
+    const int p = blockIdx.x;
+    const glamr_person_t& ps = c.pb.persons[p];
+    const int len = ps.len, T = c.pb.T;
+    const size_t n0 = (size_t)p * T + ps.start;
+    for (int t = threadIdx.x; t < T; t += kScanThreads) traj_back_pre(c, p, t, acc);
+    __syncthreads();
+    block_scan_inplace(c.sc.g_xy + 2 * n0, len, 2, true, sm);
+    block_scan_inplace(c.sc.g_xy + 2 * n0 + 1, len, 2, true, sm);
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += kScanThreads) traj_back_mid(c, p, i, acc);
+    __syncthreads();
+    block_scan_inplace(c.sc.g_head + n0, len, 1, true, sm);
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += kScanThreads) traj_back_post(c, p, i, acc);
+  }
+  block_reduce_terms(acc, partial_traj + (size_t)blockIdx.x * GLAMR_NUM_TERMS, smd);
+  if (grid_last_block(ticket)) reduce_tail(c, partial_all, n_slots, reduce_buf, smd);
+}
+
 struct AdamState {
   float* m;
   float* v;
-  double* beta_pow;   // [2] running beta1^t, beta2^t ; beta_pow[2] holds the step count (as a double)
+  double* beta_pow;   // [0] beta1^t, [1] beta2^t, [2] step count (as a double)
 };
 
-__global__ void __launch_bounds__(256) losses_kernel(OptCtx c, const float* __restrict__ reduce_buf, float* __restrict__ loss_terms,
-                                                     const double* step_count, int hist_stride) {
-  if (threadIdx.x == 0) {
-    if (hist_stride > 0) loss_terms += (size_t)step_count[0] * hist_stride;
-    double total = 0.0;
-    for (int k = 0; k < GLAMR_NUM_TERMS; ++k) {
-      float val = 0.0f;
-      if (c.pb.term_enabled[k]) {
-        val = reduce_buf[c.pb.n_params + k] / c.pb.term_norm[k];
-        if (!c.pb.term_monitor[k]) total += (double)val * (double)c.pb.term_weight[k];
-      }
-      loss_terms[k] = val;
+__device__ void write_losses(const OptCtx& c, const float* reduce_buf, float* loss_terms) {
+  double total = 0.0;
+  for (int k = 0; k < GLAMR_NUM_TERMS; ++k) {
+    float val = 0.0f;
+    if (c.pb.term_enabled[k]) {
+      val = reduce_buf[c.pb.n_params + k] / c.pb.term_norm[k];
+      if (!c.pb.term_monitor[k]) total += (double)val * (double)c.pb.term_weight[k];
     }
-    loss_terms[GLAMR_NUM_TERMS] = (float)total;
+    loss_terms[k] = val;
   }
+  loss_terms[GLAMR_NUM_TERMS] = (float)total;
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(OptCtx c, float* __restrict__ theta, const float* __restrict__ reduce_buf, float lr,
-                                                   AdamState ad, double lr_d) {
-  // every thread derives the same bias corrections from the running powers; block 0 advances them afterwards
-  const double b1 = ad.beta_pow[0] * 0.9, b2 = ad.beta_pow[1] * 0.999;
-  const float bc1 = (float)(1.0 - b1);
+__global__ void __launch_bounds__(32) losses_kernel(OptCtx c, const float* __restrict__ reduce_buf, float* __restrict__ loss_terms) {
+  if (threadIdx.x == 0) write_losses(c, reduce_buf, loss_terms);
+}
+
+// loss terms (block 0) + torch.optim.Adam step; the last CTA to finish advances the step count / beta powers
+__global__ void __launch_bounds__(256) apply_kernel(OptCtx c, float* __restrict__ theta, const float* __restrict__ reduce_buf, double lr,
+                                                    AdamState ad, float* loss_terms, int hist_stride, unsigned int* ticket) {
+  const double b1 = ad.beta_pow[0] * 0.9, b2 = ad.beta_pow[1] * 0.999, step = ad.beta_pow[2];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_terms) write_losses(c, reduce_buf, loss_terms + (hist_stride > 0 ? (size_t)step * hist_stride : 0));
   const float bc2s = (float)sqrt(1.0 - b2);
-  const float step_size = (float)(lr_d / (1.0 - b1));
+  const float step_size = (float)(lr / (1.0 - b1));
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.pb.n_params; i += gridDim.x * blockDim.x) {
     if (!c.pb.active[i]) continue;
     const float g = reduce_buf[i];
@@ -181,13 +246,11 @@ __global__ void __launch_bounds__(256) adam_kernel(OptCtx c, float* __restrict__
     ad.m[i] = m;
     ad.v[i] = v;
   }
-  (void)bc1;
-  (void)lr;
-}
-__global__ void adam_advance_kernel(AdamState ad) {
-  ad.beta_pow[0] *= 0.9;
-  ad.beta_pow[1] *= 0.999;
-  ad.beta_pow[2] += 1.0;
+  if (grid_last_block(ticket) && threadIdx.x == 0) {
+    ad.beta_pow[0] = b1;
+    ad.beta_pow[1] = b2;
+    ad.beta_pow[2] = step + 1.0;
+  }
 }
 
 }  // namespace glamr
@@ -202,12 +265,15 @@ struct glamr_opt {
   SmplWorkspace ws;
   AdamState adam;
   double* partial;
-  int n_slots, slots_res, slots_cam;
+  int n_slots, slots_res, slots_cam, cam_blocks;   // partial-sum slots: residual CTAs | P + cam_blocks (traj/cam kernel) | slots_cam (mode 3)
+  unsigned int* tickets;                           // [2] last-block-done counters (backward tail, apply)
   void* arena;
   size_t arena_bytes;
   float gs[GLAMR_NUM_TERMS];
   int timing;                 // != 0: bracket the LBS kernel with events (bench / roofline only, not graph-capturable)
   cudaEvent_t ev_lbs0, ev_lbs1;
+  cudaEvent_t ev[24];         // timing == 2: one event after every launch of glamr_opt_backward / glamr_opt_apply
+  int n_ev;
 };
 
 extern "C" size_t glamr_sizeof_person(void) { return sizeof(glamr_person_t); }
@@ -238,14 +304,16 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   st->pb = *pb;
   compute_gs(st);
   const size_t N = (size_t)pb->P * pb->T, T = pb->T, J = pb->J;
-  st->slots_res = (int)((N + kFrameThreads - 1) / kFrameThreads);
+  st->slots_res = (int)((N + kFrameThreads / 32 - 1) / (kFrameThreads / 32));
   st->slots_cam = (int)((T + kFrameThreads - 1) / kFrameThreads);
-  st->n_slots = st->slots_res + st->slots_cam + pb->P;
+  st->cam_blocks = (int)((T + kScanThreads - 1) / kScanThreads);
+  st->n_slots = st->slots_res + pb->P + st->cam_blocks + st->slots_cam;
   // one arena for all scratch (floats), doubles first for alignment
   size_t floats = 0;
   auto take = [&](size_t nfl) { size_t o = floats; floats += (nfl + 63) & ~(size_t)63; return o; };
   const size_t o_partial = take((size_t)st->n_slots * GLAMR_NUM_TERMS * 2);
-  const size_t o_beta = take(4);
+  const size_t o_beta = take(8);
+  const size_t o_ticket = take(4);
   const size_t o_heading = take(N), o_xy = take(2 * N), o_tl = take(11 * N), o_ob = take(3 * N), o_tb = take(3 * N),
                o_ow = take(3 * N), o_tw = take(3 * N), o_cam = take(12 * T), o_caminv = take(12 * T), o_camd6 = take(6 * T),
                o_jw = take(N * J * 3), o_kp = take(N * J * 2), o_ociw = take(3 * N), o_tciw = take(3 * N), o_go = take(3 * N),
@@ -260,6 +328,7 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   float* b = (float*)st->arena;
   st->partial = (double*)(b + o_partial);
   st->adam.beta_pow = (double*)(b + o_beta);
+  st->tickets = (unsigned int*)(b + o_ticket);
   st->sc.heading = b + o_heading; st->sc.xy = b + o_xy; st->sc.traj_local = b + o_tl; st->sc.orient_base = b + o_ob;
   st->sc.trans_base = b + o_tb; st->sc.orient_world = b + o_ow; st->sc.trans_world = b + o_tw; st->sc.cam = b + o_cam;
   st->sc.cam_inv = b + o_caminv; st->sc.cam_d6 = b + o_camd6; st->sc.joints_world = b + o_jw; st->sc.kp_pred = b + o_kp;
@@ -280,6 +349,7 @@ extern "C" int glamr_opt_kernel_timing(glamr_opt_t* st, int enable) {
   if (enable && !st->ev_lbs0) {
     GLAMR_CUDA_TRY(cudaEventCreate(&st->ev_lbs0));
     GLAMR_CUDA_TRY(cudaEventCreate(&st->ev_lbs1));
+    for (int i = 0; i < 24; ++i) GLAMR_CUDA_TRY(cudaEventCreate(&st->ev[i]));
   }
   st->timing = enable;
   return GLAMR_OK;
@@ -292,9 +362,19 @@ extern "C" int glamr_opt_last_lbs_ms(glamr_opt_t* st, float* ms) {
   return GLAMR_OK;
 }
 
+// timing == 2: durations (ms) between consecutive marks of the last glamr_opt_backward (+ apply) call sequence
+extern "C" int glamr_opt_kernel_times(glamr_opt_t* st, float* ms, int* n) {
+  if (!st || !ms || !n || !st->ev_lbs0) return GLAMR_EINVAL;
+  if (st->n_ev < 2) { *n = 0; return GLAMR_OK; }
+  GLAMR_CUDA_TRY(cudaEventSynchronize(st->ev[st->n_ev - 1]));
+  for (int i = 0; i + 1 < st->n_ev; ++i) GLAMR_CUDA_TRY(cudaEventElapsedTime(&ms[i], st->ev[i], st->ev[i + 1]));
+  *n = st->n_ev - 1;
+  return GLAMR_OK;
+}
+
 extern "C" int glamr_opt_destroy(glamr_opt_t* st) {
   if (!st) return GLAMR_OK;
-  if (st->ev_lbs0) { cudaEventDestroy(st->ev_lbs0); cudaEventDestroy(st->ev_lbs1); }
+  if (st->ev_lbs0) { cudaEventDestroy(st->ev_lbs0); cudaEventDestroy(st->ev_lbs1); for (int i = 0; i < 24; ++i) cudaEventDestroy(st->ev[i]); }
   cudaFree(st->arena);
   free(st);
   return GLAMR_OK;
@@ -317,56 +397,68 @@ extern "C" int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* pb,
 
 extern "C" size_t glamr_opt_reduce_count(const glamr_opt_t* st) { return st ? (size_t)st->pb.n_params + GLAMR_NUM_TERMS : 0; }
 
+#define GLAMR_MARK() do { if (st->timing == 2 && st->n_ev < 24) GLAMR_CUDA_TRY(cudaEventRecord(st->ev[st->n_ev++], s)); } while (0)
+
 extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream) {
   if (!st || !theta || !reduce_buf) return GLAMR_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
+  st->n_ev = 0;
+  GLAMR_MARK();
   const glamr_problem_t& pb = st->pb;
   const int N = pb.P * pb.T;
   OptCtx c = make_ctx(st, theta, reduce_buf);
   GLAMR_CUDA_TRY(cudaMemsetAsync(reduce_buf, 0, sizeof(float) * ((size_t)pb.n_params + GLAMR_NUM_TERMS), s));
-  traj_forward_kernel<<<pb.P, kScanThreads, 0, s>>>(c);
+  const bool from_persons = pb.cam_mode == GLAMR_CAM_FROM_PERSONS;
+  traj_cam_forward_kernel<<<pb.P + st->cam_blocks, kScanThreads, 0, s>>>(c, from_persons ? 0 : 1);
   GLAMR_LAUNCH_CHECK();
-  cam_forward_kernel<<<st->slots_cam, kFrameThreads, 0, s>>>(c);
-  GLAMR_LAUNCH_CHECK();
-  // SMPL for the persons this rank owns (global_recon_model.py:517-524)
+  GLAMR_MARK();
+  if (from_persons) {          // the camera is the mean of the persons' world transforms: needs traj_forward of all persons
+    cam_forward_kernel<<<st->slots_cam, kFrameThreads, 0, s>>>(c);
+    GLAMR_LAUNCH_CHECK();
+  }
+  GLAMR_MARK();
+  // SMPL for the persons this rank owns (global_recon_model.py:517-524); tile-major scratch (A, pf) is local to the launch
   const int n_begin = pb.p_begin * pb.T, n_end = pb.p_end * pb.T;
+  SmplWorkspace wo = st->ws;
+  wo.jposed += (size_t)n_begin * kNJ * 3;
+  wo.vcompact += (size_t)n_begin * st->smpl.S * 3;
+  wo.root_raw += (size_t)n_begin * 3;
   if (n_end > n_begin) {
-    SmplWorkspace w = st->ws;
-    // the workspace is indexed by the global frame-person index; kernels take [0, n) so offset the pointers
-    SmplWorkspace wo = w;
-    wo.A += (size_t)n_begin * kNJ * 12; wo.pf += (size_t)n_begin * kPFPad; wo.jposed += (size_t)n_begin * kNJ * 3;
-    wo.vcompact += (size_t)n_begin * st->smpl.S * 3; wo.root_raw += (size_t)n_begin * 3;
     const int nn = n_end - n_begin;
     int rc;
     if ((rc = launch_pose_prep(st->smpl, nn, st->sc.orient_world + (size_t)n_begin * 3, pb.smpl_pose_all + (size_t)n_begin * 69,
                                pb.smpl_beta_all + (size_t)n_begin * kNB, 1, wo, s))) return rc;
+    GLAMR_MARK();
     if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
     if ((rc = launch_lbs(st->smpl, 0, nn, pb.smpl_beta_all + (size_t)n_begin * kNB, wo, nullptr, s))) return rc;
     if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
-    if ((rc = launch_joints_finalize(st->smpl, nn, 0, st->sc.trans_world + (size_t)n_begin * 3,
-                                     pb.scale_all ? pb.scale_all + n_begin : nullptr, wo,
-                                     st->sc.joints_world + (size_t)n_begin * pb.J * 3, s))) return rc;
+    GLAMR_MARK();
   }
-  frame_residuals_kernel<<<st->slots_res, kFrameThreads, 0, s>>>(c, st->partial);
+  double* part_res = st->partial;
+  double* part_traj = st->partial + (size_t)st->slots_res * GLAMR_NUM_TERMS;
+  double* part_cam3 = part_traj + (size_t)(pb.P + st->cam_blocks) * GLAMR_NUM_TERMS;
+  frame_residuals_kernel<<<st->slots_res, kFrameThreads, 0, s>>>(c, st->smpl, wo, n_begin, part_res);
   GLAMR_LAUNCH_CHECK();
-  camera_backward_kernel<<<st->slots_cam, kFrameThreads, 0, s>>>(c, st->partial + (size_t)st->slots_res * GLAMR_NUM_TERMS);
-  GLAMR_LAUNCH_CHECK();
-  if (pb.cam_mode == GLAMR_CAM_FROM_PERSONS) {
+  GLAMR_MARK();
+  if (from_persons) {
+    camera_backward_kernel<<<st->slots_cam, kFrameThreads, 0, s>>>(c, part_cam3);
+    GLAMR_LAUNCH_CHECK();
     camera_scatter_kernel<<<st->slots_cam, kFrameThreads, 0, s>>>(c);
     GLAMR_LAUNCH_CHECK();
+    GLAMR_MARK();
   }
-  traj_backward_kernel<<<pb.P, kScanThreads, 0, s>>>(c, st->partial + (size_t)(st->slots_res + st->slots_cam) * GLAMR_NUM_TERMS);
+  const int n_slots = st->slots_res + pb.P + st->cam_blocks + (from_persons ? st->slots_cam : 0);
+  traj_cam_backward_kernel<<<pb.P + st->cam_blocks, kScanThreads, 0, s>>>(c, from_persons ? 0 : 1, part_traj, st->partial, n_slots, reduce_buf,
+                                                                         st->tickets);
   GLAMR_LAUNCH_CHECK();
-  reduce_kernel<<<1, 256, 0, s>>>(c, st->partial, st->n_slots, reduce_buf);
-  GLAMR_LAUNCH_CHECK();
-  (void)N;
+  GLAMR_MARK();
   return GLAMR_OK;
 }
 
 extern "C" int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms, void* stream) {
   if (!st || !reduce_buf || !loss_terms) return GLAMR_EINVAL;
   OptCtx c = make_ctx(st, nullptr, nullptr);
-  losses_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c, reduce_buf, loss_terms, st->adam.beta_pow + 2, 0);
+  losses_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c, reduce_buf, loss_terms);
   GLAMR_LAUNCH_CHECK();
   return GLAMR_OK;
 }
@@ -376,15 +468,10 @@ extern "C" int glamr_opt_apply(glamr_opt_t* st, float* theta, const float* reduc
   if (!st || !theta || !reduce_buf) return GLAMR_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   OptCtx c = make_ctx(st, theta, nullptr);
-  if (loss_terms) {
-    losses_kernel<<<1, 32, 0, s>>>(c, reduce_buf, loss_terms, st->adam.beta_pow + 2, loss_hist_stride);
-    GLAMR_LAUNCH_CHECK();
-  }
   const int blocks = (st->pb.n_params + 255) / 256;
-  adam_kernel<<<blocks < 592 ? blocks : 592, 256, 0, s>>>(c, theta, reduce_buf, (float)lr, st->adam, lr);
+  apply_kernel<<<blocks < 296 ? blocks : 296, 256, 0, s>>>(c, theta, reduce_buf, lr, st->adam, loss_terms, loss_hist_stride, st->tickets + 1);
   GLAMR_LAUNCH_CHECK();
-  adam_advance_kernel<<<1, 1, 0, s>>>(st->adam);
-  GLAMR_LAUNCH_CHECK();
+  GLAMR_MARK();
   return GLAMR_OK;
 }
 
@@ -403,7 +490,6 @@ extern "C" int glamr_opt_read(glamr_opt_t* st, int what, const float** ptr, size
     case GLAMR_R_CAM_POSE_INV: *ptr = st->sc.cam_inv; *count = 12 * T; break;
     case GLAMR_R_JOINTS_WORLD: *ptr = st->sc.joints_world; *count = N * J * 3; break;
     case GLAMR_R_TRAJ_LOCAL: *ptr = st->sc.traj_local; *count = 11 * N; break;
-    case GLAMR_R_SMPL_A: *ptr = st->ws.A; *count = N * kNJ * 12; break;
     default: return GLAMR_EINVAL;
   }
   return GLAMR_OK;

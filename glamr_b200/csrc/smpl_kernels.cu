@@ -49,11 +49,12 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(SmplDev m, int n, const 
     J[c] = v;
   }
   if (lane >= 1 && lane < kNJ) {
-    float* pf = w.pf + (size_t)f * kPFPad + (lane - 1) * 9;
+    // pose feature (R_j - I), stored tile-major [n/32][chunk = j-1][k][n%32] so the LBS kernel fetches a CTA's
+    // [9 x 32] chunk with one bulk copy
+    float* pf = w.pf + (((size_t)(f >> 5) * kNChunks + (lane - 1)) * kChunkK) * 32 + (f & 31);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) pf[k] = R[k] - ((k % 4 == 0) ? 1.0f : 0.0f);
+    for (int k = 0; k < 9; ++k) pf[k * 32] = R[k] - ((k % 4 == 0) ? 1.0f : 0.0f);
   }
-  if (lane == 0) w.pf[(size_t)f * kPFPad + kPF] = 0.0f;
 
   float GR[9], Gt[3];
 #pragma unroll
@@ -86,89 +87,105 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(SmplDev m, int n, const 
     jp[0] = Gt[0]; jp[1] = Gt[1]; jp[2] = Gt[2];
     float GJ[3];
     mat3_vec(GR, J, GJ);
-    float* A = w.A + ((size_t)f * kNJ + j) * 12;
+    // A_j (3x4 row-major, 12 floats) stored tile-major and frame-minor: [n/32][j][c][n%32], so the LBS kernel fetches
+    // a CTA's [24][12][32] tile with one bulk copy and reads it with the frame on the lane axis (conflict free)
+    float* A = w.A + (((size_t)(f >> 5) * kNJ + j) * 12) * 32 + (f & 31);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      A[i * 4 + 0] = GR[i * 3 + 0];
-      A[i * 4 + 1] = GR[i * 3 + 1];
-      A[i * 4 + 2] = GR[i * 3 + 2];
-      A[i * 4 + 3] = Gt[i] - GJ[i];
+      A[(i * 4 + 0) * 32] = GR[i * 3 + 0];
+      A[(i * 4 + 1) * 32] = GR[i * 3 + 1];
+      A[(i * 4 + 2) * 32] = GR[i * 3 + 2];
+      A[(i * 4 + 3) * 32] = Gt[i] - GJ[i];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ lbs_kernel
-// CTA = 128 vertices x 32 frame-persons, 256 threads: thread = 1 vertex x 16 frames (48 FP32 accumulators).
+// CTA = 128 vertices x 32 frame-persons, 128 threads (4 warps).  Warp w owns frames 8w..8w+7, lane l owns vertices
+// 4l..4l+3 of the tile: a 12 (columns) x 8 (frames) register tile = 96 FP32 accumulators per thread.
 //   v_posed = v_template + shapedirs.beta + posedirs^T.pose_feature           lbs.py:240,256-267
 //   vert    = (sum_k w_k A_k) [v_posed; 1]                                    lbs.py:273-284
-// The CTA's posedirs slab [207][384] is streamed L2 -> shared memory in 23 chunks of 9 rows (13,824 B contiguous
-// each, thanks to the tile-major re-layout) by the TMA engine (cp.async.bulk + mbarrier), double buffered.
+// Why this shape: the kernel is shared-memory-bandwidth bound unless the register tile is large.  Per k a thread reads
+// 12 posedirs values (3 LDS.128, distinct per lane) + 8 pose-feature values (2 LDS.128, warp-broadcast) = 20 wavefronts
+// per warp for 96 FFMA (0.21 wavefronts/FFMA, below the 0.25 the LSU can sustain next to 4 FFMA/clk); the first
+// version (3 x 16 tile) needed 19 wavefronts per 48 FFMA and stalled on the LSU (profiles/lbs_kernel_r01.md).
+// All operands arrive by 1-D bulk TMA (cp.async.bulk + mbarrier): the CTA's posedirs slab [207][384] in 23 chunks of
+// 9 rows (13,824 B contiguous thanks to the tile-major re-layout), the matching [9][32] pose-feature chunk, and the
+// A tile [32][24][12]; a 3-stage full/empty mbarrier ring replaces __syncthreads in the main loop.
 constexpr int kFramesPerCta = 32;
-constexpr int kFramesPerThread = 16;
-constexpr int kLbsThreads = 256;
-constexpr int kChunkFloats = kChunkK * kTileCols;                 // 3456
+constexpr int kFramesPerWarp = 8;
+constexpr int kVertsPerThread = 4;
+constexpr int kLbsThreads = 128;
+constexpr int kMaxStages = 4;
+constexpr int kChunkFloats = kChunkK * kTileCols;                 // 3456 posedirs floats per stage
 constexpr uint32_t kChunkBytes = kChunkFloats * sizeof(float);    // 13,824
-constexpr int kLbsSmemFloats = 2 * kChunkFloats + 2 * kChunkK * kFramesPerCta + kFramesPerCta * kNJ * 12 + kFramesPerCta * kNB;
-constexpr size_t kLbsSmemBytes = kLbsSmemFloats * sizeof(float) + 2 * sizeof(uint64_t);
+constexpr int kPfChunkFloats = kChunkK * kFramesPerCta;           // 288 pose-feature floats per stage
+constexpr uint32_t kPfChunkBytes = kPfChunkFloats * sizeof(float);
+constexpr int kATileFloats = kFramesPerCta * kNJ * 12;            // 9216
+constexpr int kVpFloats = kVTile * 3 * kFramesPerCta;            // 12,288: v_posed tile handed from the GEMM phase to the skinning phase
+__host__ __device__ constexpr int stage_region_floats(int stages) { return (stages * (kChunkFloats + kPfChunkFloats) > kVpFloats) ? stages * (kChunkFloats + kPfChunkFloats) : kVpFloats; }
+constexpr size_t lbs_smem_bytes(int stages) { return (size_t)(stage_region_floats(stages) + kATileFloats + kFramesPerCta * kNB) * sizeof(float) + (2 * kMaxStages + 1) * sizeof(uint64_t); }
 
-template <int KREG>
+template <int KREG, int kStages>
 __global__ void __launch_bounds__(kLbsThreads, 2)
-lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, SmplWorkspace w, float* __restrict__ vertices) {
+lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, SmplWorkspace w, float* __restrict__ vertices, int dbg) {
+  constexpr int kStageRegionFloats = stage_region_floats(kStages);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* PDs = reinterpret_cast<float*>(smem_raw);              // [2][9][384]
-  float* pfs = PDs + 2 * kChunkFloats;                           // [2][9][32]
-  float* As = pfs + 2 * kChunkK * kFramesPerCta;                 // [32][24][12]
-  float* bs = As + kFramesPerCta * kNJ * 12;                     // [32][10]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bs + kFramesPerCta * kNB);
+  float* PDs = reinterpret_cast<float*>(smem_raw);              // [kStages][9][384]
+  float* pfs = PDs + kStages * kChunkFloats;                     // [kStages][9][32]
+  float* As = PDs + kStageRegionFloats;                          // [24][12][32]  (frame-minor)
+  float* bs = As + kATileFloats;                                 // [32][10]
+  uint64_t* full = reinterpret_cast<uint64_t*>(bs + kFramesPerCta * kNB);   // [kStages]
+  uint64_t* empty = full + kStages;                              // [kStages]
+  uint64_t* abar = empty + kStages;                              // A tile
 
   const int tid = threadIdx.x;
-  const int vl = tid & (kVTile - 1);
-  const int fg = tid >> 7;
+  const int lane = tid & 31;
+  const int wf = (tid >> 5) * kFramesPerWarp;                   // first frame (within the tile) of this warp
   const int vtile = blockIdx.x;
   const int f0 = n_begin + blockIdx.y * kFramesPerCta;
-  const int gv = vtile * kVTile + vl;
+  const int gv0 = vtile * kVTile + lane * kVertsPerThread;      // first of this thread's 4 vertices
   const float* pd_slab = m.pd_tiles + (size_t)vtile * kPF * kTileCols;
+  const float* pf_slab = w.pf + (size_t)(f0 >> 5) * kNChunks * kPfChunkFloats;
 
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kLbsThreads / 32); }
+    mbar_init(abar, 1);
     mbar_fence_init();
   }
   __syncthreads();
+  auto issue_chunk = [&](int c) {      // producer: one elected thread, two bulk copies per stage
+    const int s = c % kStages;
+    mbar_expect_tx(&full[s], kChunkBytes + kPfChunkBytes);
+    tma_bulk_g2s(PDs + s * kChunkFloats, pd_slab + (size_t)c * kChunkFloats, kChunkBytes, &full[s]);
+    tma_bulk_g2s(pfs + s * kPfChunkFloats, pf_slab + (size_t)c * kPfChunkFloats, kPfChunkBytes, &full[s]);
+  };
   if (tid == 0) {
-    mbar_expect_tx(&bars[0], kChunkBytes);
-    tma_bulk_g2s(PDs, pd_slab, kChunkBytes, &bars[0]);
-  }
-  for (int e = tid; e < kFramesPerCta * kNJ * 12; e += kLbsThreads) {
-    const int f = e / (kNJ * 12), r = e - f * (kNJ * 12);
-    const int n = f0 + f;
-    As[e] = (n < n_end) ? w.A[(size_t)n * kNJ * 12 + r] : 0.0f;
+    mbar_expect_tx(abar, (uint32_t)kATileFloats * sizeof(float));
+    tma_bulk_g2s(As, w.A + (size_t)(f0 >> 5) * kATileFloats, (uint32_t)kATileFloats * sizeof(float), abar);
+#pragma unroll
+    for (int c = 0; c < kStages - 1; ++c) issue_chunk(c);
   }
   for (int e = tid; e < kFramesPerCta * kNB; e += kLbsThreads) {
     const int f = e / kNB, l = e - f * kNB;
     const int n = f0 + f;
     bs[e] = (n < n_end) ? betas[(size_t)n * kNB + l] : 0.0f;
   }
-  auto load_pf_chunk = [&](int c, int s) {
-    for (int e = tid; e < kChunkK * kFramesPerCta; e += kLbsThreads) {
-      const int f = e / kChunkK, k = e - f * kChunkK;
-      const int n = f0 + f;
-      pfs[s * kChunkK * kFramesPerCta + k * kFramesPerCta + f] = (n < n_end) ? w.pf[(size_t)n * kPFPad + c * kChunkK + k] : 0.0f;
-    }
-  };
-  load_pf_chunk(0, 0);
+  __syncthreads();
 
-  float acc[kFramesPerThread][3];
-  {
+  // acc[f][c]: c = 3 * vertex + coord over the thread's 4 vertices
+  float acc[kFramesPerWarp][12];
+#pragma unroll
+  for (int v = 0; v < kVertsPerThread; ++v) {
     float sdv[30];
-    const float* sd = m.shapedirs + (size_t)gv * 30;
+    const float* sd = m.shapedirs + (size_t)(gv0 + v) * 30;
 #pragma unroll
     for (int k = 0; k < 30; ++k) sdv[k] = sd[k];
-    const float vt0 = m.v_template[gv * 3 + 0], vt1 = m.v_template[gv * 3 + 1], vt2 = m.v_template[gv * 3 + 2];
-    __syncthreads();
+    const float vt0 = m.v_template[(gv0 + v) * 3 + 0], vt1 = m.v_template[(gv0 + v) * 3 + 1], vt2 = m.v_template[(gv0 + v) * 3 + 2];
 #pragma unroll
-    for (int f = 0; f < kFramesPerThread; ++f) {
-      const float* b = bs + (fg * kFramesPerThread + f) * kNB;
+    for (int f = 0; f < kFramesPerWarp; ++f) {
+      const float* b = bs + (wf + f) * kNB;
       float a0 = vt0, a1 = vt1, a2 = vt2;
 #pragma unroll
       for (int l = 0; l < kNB; ++l) {
@@ -177,88 +194,94 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
         a1 = fmaf(sdv[10 + l], bl, a1);
         a2 = fmaf(sdv[20 + l], bl, a2);
       }
-      acc[f][0] = a0; acc[f][1] = a1; acc[f][2] = a2;
+      acc[f][3 * v + 0] = a0; acc[f][3 * v + 1] = a1; acc[f][3 * v + 2] = a2;
     }
   }
 
   for (int c = 0; c < kNChunks; ++c) {
-    const int s = c & 1;
-    if (c + 1 < kNChunks) {
-      if (tid == 0) {
-        mbar_expect_tx(&bars[s ^ 1], kChunkBytes);
-        tma_bulk_g2s(PDs + (s ^ 1) * kChunkFloats, pd_slab + (size_t)(c + 1) * kChunkFloats, kChunkBytes, &bars[s ^ 1]);
-      }
-      load_pf_chunk(c + 1, s ^ 1);
+    const int s = c % kStages;
+    if (tid == 0 && c + kStages - 1 < kNChunks) {
+      // the stage about to be refilled was last read for chunk c-1: wait until every warp released it
+      if (c >= 1) mbar_wait(&empty[(c + kStages - 1) % kStages], ((c - 1) / kStages) & 1);
+      issue_chunk(c + kStages - 1);
     }
-    mbar_wait(&bars[s], (c >> 1) & 1);
-    const float* P = PDs + s * kChunkFloats + 3 * vl;
-    const float* F = pfs + s * kChunkK * kFramesPerCta + fg * kFramesPerThread;
+    mbar_wait(&full[s], (c / kStages) & 1);
+    const float4* P = reinterpret_cast<const float4*>(PDs + s * kChunkFloats + 12 * lane);
+    const float4* F = reinterpret_cast<const float4*>(pfs + s * kPfChunkFloats + wf);
+    if (!(dbg & 1))
 #pragma unroll
     for (int k = 0; k < kChunkK; ++k) {
-      const float p0 = P[k * kTileCols + 0], p1 = P[k * kTileCols + 1], p2 = P[k * kTileCols + 2];
+      const float4 p0 = P[k * (kTileCols / 4) + 0], p1 = P[k * (kTileCols / 4) + 1], p2 = P[k * (kTileCols / 4) + 2];
+      const float4 q0 = F[k * (kFramesPerCta / 4) + 0], q1 = F[k * (kFramesPerCta / 4) + 1];
+      const float pv[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+      const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-      for (int f4 = 0; f4 < kFramesPerThread / 4; ++f4) {
-        const float4 q = *reinterpret_cast<const float4*>(F + k * kFramesPerCta + f4 * 4);
-        acc[f4 * 4 + 0][0] = fmaf(q.x, p0, acc[f4 * 4 + 0][0]);
-        acc[f4 * 4 + 0][1] = fmaf(q.x, p1, acc[f4 * 4 + 0][1]);
-        acc[f4 * 4 + 0][2] = fmaf(q.x, p2, acc[f4 * 4 + 0][2]);
-        acc[f4 * 4 + 1][0] = fmaf(q.y, p0, acc[f4 * 4 + 1][0]);
-        acc[f4 * 4 + 1][1] = fmaf(q.y, p1, acc[f4 * 4 + 1][1]);
-        acc[f4 * 4 + 1][2] = fmaf(q.y, p2, acc[f4 * 4 + 1][2]);
-        acc[f4 * 4 + 2][0] = fmaf(q.z, p0, acc[f4 * 4 + 2][0]);
-        acc[f4 * 4 + 2][1] = fmaf(q.z, p1, acc[f4 * 4 + 2][1]);
-        acc[f4 * 4 + 2][2] = fmaf(q.z, p2, acc[f4 * 4 + 2][2]);
-        acc[f4 * 4 + 3][0] = fmaf(q.w, p0, acc[f4 * 4 + 3][0]);
-        acc[f4 * 4 + 3][1] = fmaf(q.w, p1, acc[f4 * 4 + 3][1]);
-        acc[f4 * 4 + 3][2] = fmaf(q.w, p2, acc[f4 * 4 + 3][2]);
+      for (int f = 0; f < kFramesPerWarp; ++f)
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) acc[f][cc] = fmaf(qv[f], pv[cc], acc[f][cc]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  // ---- hand the v_posed tile to the skinning phase through shared memory (the stage buffers are free now).
+  // Layout VP[row = vertex*3 + coord][32 frames] with the 4-frame chunk index XOR-swizzled by the writing lane so that
+  // both the STS.128 here (lanes = vertices) and the LDS.32 below (lanes = frames) are bank-conflict free.
+  __syncthreads();
+  float* VP = PDs;
+#pragma unroll
+  for (int v = 0; v < kVertsPerThread; ++v)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      const int row = (lane * kVertsPerThread + v) * 3 + cc;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int chunk = ((wf >> 2) + h) ^ (lane & 7);
+        *reinterpret_cast<float4*>(VP + row * 32 + chunk * 4) =
+            make_float4(acc[4 * h + 0][3 * v + cc], acc[4 * h + 1][3 * v + cc], acc[4 * h + 2][3 * v + cc], acc[4 * h + 3][3 * v + cc]);
       }
     }
-    __syncthreads();
-  }
+  mbar_wait(abar, 0);
+  __syncthreads();
 
-  // ---- skinning epilogue
-  int wj[KREG > 0 ? KREG : 1];
-  float ww[KREG > 0 ? KREG : 1];
-  if (KREG > 0) {
-#pragma unroll
-    for (int s = 0; s < KREG; ++s) {
-      wj[s] = m.skin_j[(size_t)gv * KREG + s];
-      ww[s] = m.skin_w[(size_t)gv * KREG + s];
-    }
-  }
-  const int ci = m.compact_of_vertex[gv];
-  const bool v_ok = gv < kV;
-#pragma unroll
-  for (int f = 0; f < kFramesPerThread; ++f) {
-    const int fl = fg * kFramesPerThread + f;
-    const int n = f0 + fl;
+  // ---- skinning: warp w owns vertices 32w..32w+31 of the tile, lane = frame.  Joint indices / weights are
+  // warp-uniform, A is read frame-minor: every LDS is conflict free.
+  const int fr = lane;
+  const int n = f0 + fr;
+  const bool n_ok = n < n_end;
+  if (!(dbg & 2))
+  for (int vi = (tid >> 5) * 32; vi < (tid >> 5) * 32 + 32; ++vi) {
+    const int gv = vtile * kVTile + vi;
+    if (gv >= kV) break;
+    const int ci = m.compact_of_vertex[gv];
+    const int pos = ((((fr >> 2) ^ ((vi >> 2) & 7)) << 2) | (fr & 3));
+    const float x = VP[(vi * 3 + 0) * 32 + pos], y = VP[(vi * 3 + 1) * 32 + pos], z = VP[(vi * 3 + 2) * 32 + pos];
     float T[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) T[k] = 0.0f;
     if (KREG > 0) {
+      const float4 w4 = *reinterpret_cast<const float4*>(m.skin_w + (size_t)gv * 4);
+      const uchar4 j4 = *reinterpret_cast<const uchar4*>(m.skin_j + (size_t)gv * 4);
+      const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+      const int wj[4] = {j4.x, j4.y, j4.z, j4.w};
 #pragma unroll
-      for (int s = 0; s < KREG; ++s) {
-        const float4* a = reinterpret_cast<const float4*>(As + (fl * kNJ + wj[s]) * 12);
-        const float4 a0 = a[0], a1 = a[1], a2 = a[2];
-        const float wt = ww[s];
-        T[0] = fmaf(wt, a0.x, T[0]); T[1] = fmaf(wt, a0.y, T[1]); T[2] = fmaf(wt, a0.z, T[2]); T[3] = fmaf(wt, a0.w, T[3]);
-        T[4] = fmaf(wt, a1.x, T[4]); T[5] = fmaf(wt, a1.y, T[5]); T[6] = fmaf(wt, a1.z, T[6]); T[7] = fmaf(wt, a1.w, T[7]);
-        T[8] = fmaf(wt, a2.x, T[8]); T[9] = fmaf(wt, a2.y, T[9]); T[10] = fmaf(wt, a2.z, T[10]); T[11] = fmaf(wt, a2.w, T[11]);
+      for (int s = 0; s < 4; ++s) {
+        const float* a = As + wj[s] * 12 * 32 + fr;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = fmaf(ww[s], a[k * 32], T[k]);
       }
     } else {
       for (int s = 0; s < m.K; ++s) {
         const int jj = m.skin_j[(size_t)gv * m.K + s];
         const float wt = m.skin_w[(size_t)gv * m.K + s];
-        const float* a = As + (fl * kNJ + jj) * 12;
+        const float* a = As + jj * 12 * 32 + fr;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) T[k] = fmaf(wt, a[k], T[k]);
+        for (int k = 0; k < 12; ++k) T[k] = fmaf(wt, a[k * 32], T[k]);
       }
     }
-    const float x = acc[f][0], y = acc[f][1], z = acc[f][2];
     const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
     const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
     const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
-    if (n < n_end && v_ok) {
+    if (n_ok) {
       if (vertices) {
         float* o = vertices + ((size_t)n * kV + gv) * 3;
         o[0] = ox; o[1] = oy; o[2] = oz;
@@ -274,25 +297,6 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
 // ------------------------------------------------------------------------------------------------ joints_finalize
 // One warp per frame-person: gather the mapped joints from [24 LBS | picks | extra regressed], re-root at joint 0
 // and apply scale / root translation   (lib/models/smpl.py:299-315)
-__device__ __forceinline__ void raw_joint(const SmplDev& m, const SmplWorkspace& w, int f, int idx, float* o) {
-  if (idx < kNJ) {
-    const float* p = w.jposed + ((size_t)f * kNJ + idx) * 3;
-    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-  } else if (idx < kNJ + m.n_picks) {
-    const float* p = w.vcompact + ((size_t)f * m.S + m.pick_ci[idx - kNJ]) * 3;
-    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-  } else {
-    const int r = idx - kNJ - m.n_picks;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int e = m.reg_ptr[r]; e < m.reg_ptr[r + 1]; ++e) {
-      const float* p = w.vcompact + ((size_t)f * m.S + m.reg_ci[e]) * 3;
-      const float wt = m.reg_w[e];
-      a0 = fmaf(wt, p[0], a0); a1 = fmaf(wt, p[1], a1); a2 = fmaf(wt, p[2], a2);
-    }
-    o[0] = a0; o[1] = a1; o[2] = a2;
-  }
-}
-
 __global__ void __launch_bounds__(128) joints_finalize_kernel(SmplDev m, int n, int orig_joints, const float* __restrict__ root_trans,
                                                               const float* __restrict__ root_scale, SmplWorkspace w,
                                                               float* __restrict__ joints) {
@@ -357,17 +361,24 @@ int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* 
 
 int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices, cudaStream_t s) {
   if (n_end <= n_begin) return GLAMR_OK;
+  if (n_begin % kFramesPerCta != 0) return GLAMR_EINVAL;   // the tile-major scratch is indexed by whole frame tiles
   dim3 grid(kNVTiles, (n_end - n_begin + kFramesPerCta - 1) / kFramesPerCta);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbsSmemBytes));
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbsSmemBytes));
-    attr_set = true;
+  static int stages = 0, dbg = 0;
+  if (!stages) {
+    const char* e = getenv("GLAMR_LBS_STAGES");
+    stages = (e && atoi(e) == 4) ? 4 : 3;
+    const char* d = getenv("GLAMR_LBS_DEBUG");      // measurement aid only: bit0 skips the FMA loop, bit1 the skinning phase
+    dbg = d ? atoi(d) : 0;
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbs_smem_bytes(3)));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbs_smem_bytes(3)));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbs_smem_bytes(4)));
   }
-  if (m.K == 4)
-    lbs_kernel<4><<<grid, kLbsThreads, kLbsSmemBytes, s>>>(m, n_begin, n_end, betas, w, vertices);
+  if (m.K == 4 && stages == 4)
+    lbs_kernel<4, 4><<<grid, kLbsThreads, lbs_smem_bytes(4), s>>>(m, n_begin, n_end, betas, w, vertices, dbg);
+  else if (m.K == 4)
+    lbs_kernel<4, 3><<<grid, kLbsThreads, lbs_smem_bytes(3), s>>>(m, n_begin, n_end, betas, w, vertices, dbg);
   else
-    lbs_kernel<0><<<grid, kLbsThreads, kLbsSmemBytes, s>>>(m, n_begin, n_end, betas, w, vertices);
+    lbs_kernel<0, 3><<<grid, kLbsThreads, lbs_smem_bytes(3), s>>>(m, n_begin, n_end, betas, w, vertices, dbg);
   GLAMR_LAUNCH_CHECK();
   return GLAMR_OK;
 }

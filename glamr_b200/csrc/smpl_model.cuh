@@ -31,26 +31,49 @@ struct SmplDev {
 };
 
 struct SmplWorkspace {
-  float* A;         // [n][24][12]  relative joint transforms (3x4 row-major)
-  float* pf;        // [n][208]     pose feature (R_j - I), j = 1..23
+  float* A;         // [n/32][24][12][32] relative joint transforms (3x4 row-major per joint), tile-major, frame-minor
+  float* pf;        // [n/32][23][9][32] pose feature (R_j - I), j = 1..23, tile-major for bulk TMA (208 floats per frame reserved)
   float* jposed;    // [n][24][3]   posed LBS joints
   float* vcompact;  // [n][S][3]    skinned support vertices
   float* root_raw;  // [n][3]       un-rooted joint 0 (for vertex re-rooting)
 };
 
 inline size_t smpl_workspace_floats(int n, int S) {
-  return (size_t)n * (kNJ * 12 + kPFPad + kNJ * 3 + (size_t)S * 3 + 3) + 64;
+  const size_t n32 = ((size_t)n + 31) / 32 * 32;   // the pose feature is tile-major over whole 32-frame tiles
+  return (size_t)n * (kNJ * 3 + (size_t)S * 3 + 3) + n32 * (kPFPad + kNJ * 12) + 64;
 }
 inline SmplWorkspace smpl_carve_workspace(void* base, int n, int S) {
   SmplWorkspace w;
   float* p = (float*)base;
-  w.A = p; p += (size_t)n * kNJ * 12;
-  w.pf = p; p += (size_t)n * kPFPad;
+  w.A = p; p += ((size_t)n + 31) / 32 * 32 * kNJ * 12;
+  w.pf = p; p += ((size_t)n + 31) / 32 * 32 * kPFPad;
   w.jposed = p; p += (size_t)n * kNJ * 3;
   w.vcompact = p; p += (size_t)n * S * 3;
   w.root_raw = p;
   return w;
 }
+
+#if defined(__CUDACC__)
+// un-rooted joint `idx` of [24 LBS | picks | extra regressed] for local frame-person f  (lib/models/smpl.py:299-301)
+__device__ __forceinline__ void raw_joint(const SmplDev& m, const SmplWorkspace& w, int f, int idx, float* o) {
+  if (idx < kNJ) {
+    const float* p = w.jposed + ((size_t)f * kNJ + idx) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  } else if (idx < kNJ + m.n_picks) {
+    const float* p = w.vcompact + ((size_t)f * m.S + m.pick_ci[idx - kNJ]) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  } else {
+    const int r = idx - kNJ - m.n_picks;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int e = m.reg_ptr[r]; e < m.reg_ptr[r + 1]; ++e) {
+      const float* p = w.vcompact + ((size_t)f * m.S + m.reg_ci[e]) * 3;
+      const float wt = m.reg_w[e];
+      a0 = fmaf(wt, p[0], a0); a1 = fmaf(wt, p[1], a1); a2 = fmaf(wt, p[2], a2);
+    }
+    o[0] = a0; o[1] = a1; o[2] = a2;
+  }
+}
+#endif
 
 // launches (smpl_kernels.cu); all asynchronous on `s`
 // orient may be NULL (zeros).  use_betas == 0 -> rest joints from the template only (SMPL.get_joints).

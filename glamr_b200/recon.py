@@ -480,11 +480,18 @@ class GlobalReconOptimizer:
             if opt_niters > 0:
                 one_iteration()                                  # warm-up (also sets kernel attributes) = iteration 0
                 done = 1
-                if self.use_cuda_graph and self.world == 1 and opt_niters > 2:
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        one_iteration()
-                    # capture does not execute: the captured iteration still has to run
+                if self.use_cuda_graph and opt_niters > 2:
+                    try:                                         # NCCL all-reduce is capturable too (world > 1)
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            one_iteration()
+                    except Exception as e:                       # capture is an optimisation, eager launches are equivalent
+                        if self.world == 1:
+                            raise
+                        graph = None
+                        torch.cuda.synchronize()
+                        if self.log is not None:
+                            self.log.info(f'CUDA-graph capture with NCCL unavailable ({e}); running eager iterations')
             ev0.record()
             chunk = max(int(self.log_interval), 1)
             logged = 0

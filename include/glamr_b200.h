@@ -221,6 +221,10 @@ int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms
  * and returns its duration.  The only entry point that synchronises. */
 int glamr_opt_kernel_timing(glamr_opt_t* st, int enable);
 int glamr_opt_last_lbs_ms(glamr_opt_t* st, float* ms);
+/* enable == 2: also record an event after every launch; durations (ms) between consecutive marks of the last
+ * backward (+ apply) sequence: memset, traj_fwd, cam_fwd, pose_prep, lbs, joints, residuals, cam_bwd[, scatter], traj_bwd,
+ * reduce[, losses, adam, advance] */
+int glamr_opt_kernel_times(glamr_opt_t* st, float* ms, int* n);
 
 enum glamr_read {
   GLAMR_R_ORIENT_WORLD = 0,    /* [P,T,3]   smpl_orient_world            */
