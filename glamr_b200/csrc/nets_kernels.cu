@@ -1,9 +1,10 @@
 // Learned-prior inference on sm_100a: the motion infiller (CVAE, transformer encoder/decoder over 50-frame windows,
 // motion_infiller/models/motion_infiller_vae.py:22-123,252-421,564-632) and the trajectory predictor (CVAE, MLP +
 // 2-layer bidirectional LSTM, traj_pred/models/traj_pred_vae.py:20-92,202-333; lib/models/{mlp,rnn,pos_encoding}.py).
-// Round-1 implementation: FP32 SIMT kernels (tiled SGEMM, warp LayerNorm, shared-memory attention, persistent LSTM
-// recurrence with the recurrent weights resident in registers + shared memory) so that the outputs match the
-// reference's fp32 nets to ~1e-5; the tcgen05 tensor-core GEMM path is the planned upgrade for the transformer blocks.
+// Every Linear (QKV / out-proj / FFN / MLP / LSTM input projections) runs on the tensor cores: tcgen05.mma kind::tf32
+// with a 3xTF32 split and the accumulator in TMEM (gemm_tf32x3_tcgen05_kernel); LayerNorm, softmax attention (S <= 64,
+// shared memory) and the LSTM recurrence (W_hh resident in registers + shared memory for the whole sequence) are FP32
+// SIMT kernels.  Outputs match the reference's fp32 networks to <= 1e-4 (tests/golden/nets.npz).
 // Weights are addressed by their reference state-dict names so Lightning checkpoints map 1:1.
 #include <math.h>
 #include <stdlib.h>
@@ -74,8 +75,206 @@ __global__ void __launch_bounds__(256) gemm_bias_act_kernel(int M, int N, int K,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tcgen05 GEMM (3xTF32)
+// Y = act(X W^T + b) on the 5th-generation tensor cores: tcgen05.mma.kind::tf32 with the accumulator in TMEM.
+// FP32 accuracy is kept with the 3xTF32 split  x = hi + lo (hi = tf32(x), lo = tf32(x - hi)):
+//   X W^T ~= Xhi Whi^T + Xlo Whi^T + Xhi Wlo^T     (error ~2^-21 relative: the 1e-4 parity bar of the infilled pose holds)
+// CTA = 128 threads, tile 128 (M) x 128 (N), K step 32.  Both operands are K-major (X [M,K] and W [N,K] row-major), written
+// by the CTA into shared memory in the canonical no-swizzle UMMA layout (8-row x 16-byte core matrices: element (r,k) at
+// ((k/4)*128 + r)*16 + (k%4)*4 bytes => LBO = 2048 B between K groups, SBO = 128 B between 8-row groups), made visible to
+// the async proxy with fence.proxy.async, multiplied by one elected thread (12 MMAs per K step), completion tracked with
+// tcgen05.commit -> mbarrier; the epilogue reads the 128x128 fp32 accumulator with tcgen05.ld (32x32b.x32), adds the
+// bias, applies the activation and stores.
+constexpr int TCM = 128, TCN = 128, TCK = 32;
+constexpr int kTcTileFloats = TCM * TCK;                       // 4096 floats = 16 KB per operand tile
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(const void* smem_ptr) {
+  // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout_type=0 [61,64)
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((TCM * 16) >> 4) << 16;      // leading byte offset: next 16-byte K group
+  d |= (uint64_t)(128 >> 4) << 32;             // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
+}
+
+constexpr int kTcThreads = 256;
+constexpr int kTcStages = 2;
+constexpr size_t kTcSmemBytesTotal = (size_t)kTcStages * 4 * kTcTileFloats * sizeof(float) + 64;
+
+// stage one 128x32 tile pair (X rows m0.., W rows n0.., K columns k0..k0+31) into shared memory as tf32 hi / lo
+template <bool VEC>
+__device__ __forceinline__ void tc_stage_tiles(float* st, int tid, int M, int N, int K, const float* __restrict__ X, int ldx,
+                                               const float* __restrict__ W, int m0, int n0, int k0) {
+  float* Ahi = st;
+  float* Alo = st + kTcTileFloats;
+  float* Bhi = st + 2 * kTcTileFloats;
+  float* Blo = st + 3 * kTcTileFloats;
+#pragma unroll
+  for (int i = 0; i < (TCM * TCK / 4) / kTcThreads; ++i) {
+    const int idx = tid + i * kTcThreads;
+    const int r = idx & 127, kg = idx >> 7;          // row, 16-byte K group (0..7)
+    const int k = k0 + kg * 4;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), wv = xv;
+    if (VEC) {
+      if (m0 + r < M && k < K) xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * ldx + k));
+      if (n0 + r < N && k < K) wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * K + k));
+    } else {
+      float xa[4], wa[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        xa[q] = (m0 + r < M && k + q < K) ? X[(size_t)(m0 + r) * ldx + k + q] : 0.0f;
+        wa[q] = (n0 + r < N && k + q < K) ? W[(size_t)(n0 + r) * K + k + q] : 0.0f;
+      }
+      xv = make_float4(xa[0], xa[1], xa[2], xa[3]);
+      wv = make_float4(wa[0], wa[1], wa[2], wa[3]);
+    }
+    float4 xh, xl, wh, wl;
+    split_tf32(xv.x, xh.x, xl.x); split_tf32(xv.y, xh.y, xl.y); split_tf32(xv.z, xh.z, xl.z); split_tf32(xv.w, xh.w, xl.w);
+    split_tf32(wv.x, wh.x, wl.x); split_tf32(wv.y, wh.y, wl.y); split_tf32(wv.z, wh.z, wl.z); split_tf32(wv.w, wh.w, wl.w);
+    const int off = (kg * TCM + r) * 4;
+    *reinterpret_cast<float4*>(Ahi + off) = xh;
+    *reinterpret_cast<float4*>(Alo + off) = xl;
+    *reinterpret_cast<float4*>(Bhi + off) = wh;
+    *reinterpret_cast<float4*>(Blo + off) = wl;
+  }
+}
+
+// 256 threads; two shared-memory stages: while the tensor core works on stage s (12 UTCHMMA per K step, tracked by
+// tcgen05.commit -> mbarrier[s]) all threads fetch, split and store the next K step into stage s^1.
+template <int ACT, bool VEC>
+__global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, int N, int K, const float* __restrict__ X, int ldx,
+                                                                         const float* __restrict__ W, const float* __restrict__ bias,
+                                                                         const float* __restrict__ bias2, float* __restrict__ Y, int ldy) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  float* stage0 = reinterpret_cast<float*>(tc_smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + kTcStages * 4 * kTcTileFloats);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * TCM, n0 = blockIdx.x * TCN;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  tc_stage_tiles<VEC>(stage0, tid, M, N, K, X, ldx, W, m0, n0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
+
+  const int nk = (K + TCK - 1) / TCK;
+  for (int it = 0; it < nk; ++it) {
+    const int s = it & 1;
+    float* st = stage0 + s * 4 * kTcTileFloats;
+    if (tid == 0) {
+#pragma unroll
+      for (int k8 = 0; k8 < TCK / 8; ++k8) {           // one tf32 MMA consumes K = 8 (two 16-byte K groups)
+        const size_t koff = (size_t)k8 * 2 * TCM * 4;   // floats
+        const uint64_t dah = umma_desc_kmajor_noswizzle(st + koff), dal = umma_desc_kmajor_noswizzle(st + kTcTileFloats + koff);
+        const uint64_t dbh = umma_desc_kmajor_noswizzle(st + 2 * kTcTileFloats + koff), dbl = umma_desc_kmajor_noswizzle(st + 3 * kTcTileFloats + koff);
+        umma_tf32(tmem_d, dah, dbh, idesc, (it > 0 || k8 > 0) ? 1u : 0u);
+        umma_tf32(tmem_d, dal, dbh, idesc, 1u);
+        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+      }
+      // arrive on mbarrier[s] when every MMA issued so far has completed (implies fence::before_thread_sync)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[s])) : "memory");
+    }
+    if (it + 1 < nk) {
+      // stage s^1 was consumed by the MMAs of step it-1: wait for their commit, then refill it while step `it` computes
+      if (it >= 1) mbar_wait(&bar[s ^ 1], ((it - 1) >> 1) & 1);
+      tc_stage_tiles<VEC>(stage0 + (s ^ 1) * 4 * kTcTileFloats, tid, M, N, K, X, ldx, W, m0, n0, (it + 1) * TCK);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+  }
+  mbar_wait(&bar[(nk - 1) & 1], ((nk - 1) >> 1) & 1);      // all MMAs done: the accumulator is final
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: warps 0-3 own TMEM lanes (= rows) 32w..32w+31
+  if (warp < 4) {
+    const int m = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int cc = 0; cc < TCN / 32; ++cc) {
+      if (n0 + cc * 32 >= N) break;
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, "
+          "%28, %29, %30, %31}, [%32];\n"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+            "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + cc * 32 + j;
+          if (n < N) {
+            float o = __uint_as_float(v[j]) + (bias ? bias[n] : 0.0f) + (bias2 ? bias2[n] : 0.0f);
+            if (ACT == 1) o = fmaxf(o, 0.0f);
+            Y[(size_t)m * ldy + n] = o;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TCN));
+}
+
+static int g_gemm_mode = 1;   // 1 = tcgen05 3xTF32 (default), 0 = FP32 SIMT (kept for A/B verification)
+
 static int gemm(cudaStream_t s, int M, int N, int K, const float* X, int ldx, const float* W, const float* b, const float* b2, float* Y,
                 int ldy, int act) {
+  if (g_gemm_mode == 1) {
+    static bool attr = false;
+    if (!attr) {
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
+      attr = true;
+    }
+    dim3 grid((N + TCN - 1) / TCN, (M + TCM - 1) / TCM);
+    const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)X | (uintptr_t)W) % 16 == 0);
+    if (vec) {
+      if (act == 1) gemm_tf32x3_tcgen05_kernel<1, true><<<grid, kTcThreads, kTcSmemBytesTotal, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+      else gemm_tf32x3_tcgen05_kernel<0, true><<<grid, kTcThreads, kTcSmemBytesTotal, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+    } else {
+      if (act == 1) gemm_tf32x3_tcgen05_kernel<1, false><<<grid, kTcThreads, kTcSmemBytesTotal, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+      else gemm_tf32x3_tcgen05_kernel<0, false><<<grid, kTcThreads, kTcSmemBytesTotal, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+    }
+    GLAMR_LAUNCH_CHECK();
+    return GLAMR_OK;
+  }
   dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
   if (act == 1)
     gemm_bias_act_kernel<1><<<grid, 256, 0, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
@@ -411,6 +610,23 @@ int decoder_layer(cudaStream_t s, Arena& A, const DecLayer& L, int B, int S, int
   return GLAMR_OK;
 }
 }  // namespace
+
+// Y[M,N] = act(X[M,K] W[N,K]^T + bias) -- stand-alone entry for the GEMM used by every Linear of the prior networks
+// (nn.Linear in lib/models/mlp.py:32-41, nn.MultiheadAttention projections, FFN).  mode: 1 tcgen05 3xTF32, 0 FP32 SIMT.
+extern "C" int glamr_linear_forward(int M, int N, int K, const float* X, const float* W, const float* bias, int relu, float* Y, int mode,
+                                    void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || !X || !W || !Y) return GLAMR_EINVAL;
+  const int saved = g_gemm_mode;
+  g_gemm_mode = mode;
+  const int rc = gemm((cudaStream_t)stream, M, N, K, X, K, W, bias, nullptr, Y, N, relu ? 1 : 0);
+  g_gemm_mode = saved;
+  return rc;
+}
+extern "C" int glamr_net_set_gemm_mode(int mode) {
+  if (mode != 0 && mode != 1) return GLAMR_EINVAL;
+  g_gemm_mode = mode;
+  return GLAMR_OK;
+}
 
 extern "C" int glamr_net_create(glamr_net** out) {
   if (!out) return GLAMR_EINVAL;
