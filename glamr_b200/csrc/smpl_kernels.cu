@@ -148,6 +148,33 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
   const float* pd_slab = m.pd_tiles + (size_t)vtile * kPF * kTileCols;
   const float* pf_slab = w.pf + (size_t)(f0 >> 5) * kNChunks * kPfChunkFloats;
 
+  // issue the per-vertex constant loads first: their latency overlaps the barrier set-up and the first TMA round trip
+  float sdv[kVertsPerThread][30], vt[kVertsPerThread][3];
+  {
+    const float4* sd4 = reinterpret_cast<const float4*>(m.shapedirs + (size_t)gv0 * 30);           // gv0 % 4 == 0 -> 480-byte aligned
+    float tmp[kVertsPerThread * 30];
+#pragma unroll
+    for (int q = 0; q < kVertsPerThread * 30 / 4; ++q) {
+      const float4 t4 = __ldg(sd4 + q);
+      tmp[4 * q] = t4.x; tmp[4 * q + 1] = t4.y; tmp[4 * q + 2] = t4.z; tmp[4 * q + 3] = t4.w;
+    }
+#pragma unroll
+    for (int v = 0; v < kVertsPerThread; ++v)
+#pragma unroll
+      for (int k = 0; k < 30; ++k) sdv[v][k] = tmp[v * 30 + k];
+    const float4* vt4 = reinterpret_cast<const float4*>(m.v_template + (size_t)gv0 * 3);            // 12 contiguous floats
+    const float4 a = __ldg(vt4), b = __ldg(vt4 + 1), c = __ldg(vt4 + 2);
+    vt[0][0] = a.x; vt[0][1] = a.y; vt[0][2] = a.z; vt[1][0] = a.w; vt[1][1] = b.x; vt[1][2] = b.y;
+    vt[2][0] = b.z; vt[2][1] = b.w; vt[2][2] = c.x; vt[3][0] = c.y; vt[3][1] = c.z; vt[3][2] = c.w;
+  }
+  float bpre[(kFramesPerCta * kNB + kLbsThreads - 1) / kLbsThreads];
+#pragma unroll
+  for (int i = 0; i < (kFramesPerCta * kNB + kLbsThreads - 1) / kLbsThreads; ++i) {
+    const int e = tid + i * kLbsThreads;
+    const int f = e / kNB, l = e - f * kNB;
+    const int nn = f0 + f;
+    bpre[i] = (e < kFramesPerCta * kNB && nn < n_end) ? betas[(size_t)nn * kNB + l] : 0.0f;
+  }
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kLbsThreads / 32); }
@@ -167,32 +194,28 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
 #pragma unroll
     for (int c = 0; c < kStages - 1; ++c) issue_chunk(c);
   }
-  for (int e = tid; e < kFramesPerCta * kNB; e += kLbsThreads) {
-    const int f = e / kNB, l = e - f * kNB;
-    const int n = f0 + f;
-    bs[e] = (n < n_end) ? betas[(size_t)n * kNB + l] : 0.0f;
+#pragma unroll
+  for (int i = 0; i < (kFramesPerCta * kNB + kLbsThreads - 1) / kLbsThreads; ++i) {
+    const int e = tid + i * kLbsThreads;
+    if (e < kFramesPerCta * kNB) bs[e] = bpre[i];
   }
   __syncthreads();
 
   // acc[f][c]: c = 3 * vertex + coord over the thread's 4 vertices
   float acc[kFramesPerWarp][12];
 #pragma unroll
-  for (int v = 0; v < kVertsPerThread; ++v) {
-    float sdv[30];
-    const float* sd = m.shapedirs + (size_t)(gv0 + v) * 30;
+  for (int f = 0; f < kFramesPerWarp; ++f) {
+    float bl[kNB];
 #pragma unroll
-    for (int k = 0; k < 30; ++k) sdv[k] = sd[k];
-    const float vt0 = m.v_template[(gv0 + v) * 3 + 0], vt1 = m.v_template[(gv0 + v) * 3 + 1], vt2 = m.v_template[(gv0 + v) * 3 + 2];
+    for (int l = 0; l < kNB; ++l) bl[l] = bs[(wf + f) * kNB + l];
 #pragma unroll
-    for (int f = 0; f < kFramesPerWarp; ++f) {
-      const float* b = bs + (wf + f) * kNB;
-      float a0 = vt0, a1 = vt1, a2 = vt2;
+    for (int v = 0; v < kVertsPerThread; ++v) {
+      float a0 = vt[v][0], a1 = vt[v][1], a2 = vt[v][2];
 #pragma unroll
       for (int l = 0; l < kNB; ++l) {
-        const float bl = b[l];
-        a0 = fmaf(sdv[l], bl, a0);
-        a1 = fmaf(sdv[10 + l], bl, a1);
-        a2 = fmaf(sdv[20 + l], bl, a2);
+        a0 = fmaf(sdv[v][l], bl[l], a0);
+        a1 = fmaf(sdv[v][10 + l], bl[l], a1);
+        a2 = fmaf(sdv[v][20 + l], bl[l], a2);
       }
       acc[f][3 * v + 0] = a0; acc[f][3 * v + 1] = a1; acc[f][3 * v + 2] = a2;
     }
@@ -244,51 +267,80 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
   __syncthreads();
 
   // ---- skinning: warp w owns vertices 32w..32w+31 of the tile, lane = frame.  Joint indices / weights are
-  // warp-uniform, A is read frame-minor: every LDS is conflict free.
+  // warp-uniform (prefetched one vertex per lane, broadcast with shuffles), A is read frame-minor: every LDS is
+  // conflict free.
   const int fr = lane;
   const int n = f0 + fr;
   const bool n_ok = n < n_end;
-  if (!(dbg & 2))
-  for (int vi = (tid >> 5) * 32; vi < (tid >> 5) * 32 + 32; ++vi) {
-    const int gv = vtile * kVTile + vi;
-    if (gv >= kV) break;
-    const int ci = m.compact_of_vertex[gv];
-    const int pos = ((((fr >> 2) ^ ((vi >> 2) & 7)) << 2) | (fr & 3));
-    const float x = VP[(vi * 3 + 0) * 32 + pos], y = VP[(vi * 3 + 1) * 32 + pos], z = VP[(vi * 3 + 2) * 32 + pos];
-    float T[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) T[k] = 0.0f;
+  const int vbase = (tid >> 5) * 32;
+  if (!(dbg & 2)) {
     if (KREG > 0) {
-      const float4 w4 = *reinterpret_cast<const float4*>(m.skin_w + (size_t)gv * 4);
-      const uchar4 j4 = *reinterpret_cast<const uchar4*>(m.skin_j + (size_t)gv * 4);
-      const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-      const int wj[4] = {j4.x, j4.y, j4.z, j4.w};
+      const int gvl = min(vtile * kVTile + vbase + lane, kVPad - 1);
+      const float4 my_w = *reinterpret_cast<const float4*>(m.skin_w + (size_t)gvl * 4);
+      const unsigned int my_j = *reinterpret_cast<const unsigned int*>(m.skin_j + (size_t)gvl * 4);
+      const int my_ci = m.compact_of_vertex[gvl];
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int vi = vbase + i;
+        const int gv = vtile * kVTile + vi;
+        if (gv >= kV) break;
+        const float w0 = __shfl_sync(0xffffffffu, my_w.x, i), w1 = __shfl_sync(0xffffffffu, my_w.y, i);
+        const float w2 = __shfl_sync(0xffffffffu, my_w.z, i), w3 = __shfl_sync(0xffffffffu, my_w.w, i);
+        const unsigned int jj = __shfl_sync(0xffffffffu, my_j, i);
+        const int ci = __shfl_sync(0xffffffffu, my_ci, i);
+        const int pos = ((((fr >> 2) ^ ((vi >> 2) & 7)) << 2) | (fr & 3));
+        const float x = VP[(vi * 3 + 0) * 32 + pos], y = VP[(vi * 3 + 1) * 32 + pos], z = VP[(vi * 3 + 2) * 32 + pos];
+        const float* a0 = As + (jj & 0xff) * 12 * 32 + fr;
+        const float* a1 = As + ((jj >> 8) & 0xff) * 12 * 32 + fr;
+        const float* a2 = As + ((jj >> 16) & 0xff) * 12 * 32 + fr;
+        const float* a3 = As + ((jj >> 24) & 0xff) * 12 * 32 + fr;
+        float T[12];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const float* a = As + wj[s] * 12 * 32 + fr;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) T[k] = fmaf(ww[s], a[k * 32], T[k]);
+        for (int k = 0; k < 12; ++k) T[k] = fmaf(w3, a3[k * 32], fmaf(w2, a2[k * 32], fmaf(w1, a1[k * 32], w0 * a0[k * 32])));
+        const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+        const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+        const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+        if (n_ok) {
+          if (vertices) {
+            float* o = vertices + ((size_t)n * kV + gv) * 3;
+            o[0] = ox; o[1] = oy; o[2] = oz;
+          }
+          if (ci >= 0) {
+            float* o = w.vcompact + ((size_t)n * m.S + ci) * 3;
+            o[0] = ox; o[1] = oy; o[2] = oz;
+          }
+        }
       }
     } else {
-      for (int s = 0; s < m.K; ++s) {
-        const int jj = m.skin_j[(size_t)gv * m.K + s];
-        const float wt = m.skin_w[(size_t)gv * m.K + s];
-        const float* a = As + jj * 12 * 32 + fr;
+      for (int vi = vbase; vi < vbase + 32; ++vi) {
+        const int gv = vtile * kVTile + vi;
+        if (gv >= kV) break;
+        const int ci = m.compact_of_vertex[gv];
+        const int pos = ((((fr >> 2) ^ ((vi >> 2) & 7)) << 2) | (fr & 3));
+        const float x = VP[(vi * 3 + 0) * 32 + pos], y = VP[(vi * 3 + 1) * 32 + pos], z = VP[(vi * 3 + 2) * 32 + pos];
+        float T[12];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) T[k] = fmaf(wt, a[k * 32], T[k]);
-      }
-    }
-    const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
-    const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
-    const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
-    if (n_ok) {
-      if (vertices) {
-        float* o = vertices + ((size_t)n * kV + gv) * 3;
-        o[0] = ox; o[1] = oy; o[2] = oz;
-      }
-      if (ci >= 0) {
-        float* o = w.vcompact + ((size_t)n * m.S + ci) * 3;
-        o[0] = ox; o[1] = oy; o[2] = oz;
+        for (int k = 0; k < 12; ++k) T[k] = 0.0f;
+        for (int s = 0; s < m.K; ++s) {
+          const int jj = m.skin_j[(size_t)gv * m.K + s];
+          const float wt = m.skin_w[(size_t)gv * m.K + s];
+          const float* a = As + jj * 12 * 32 + fr;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) T[k] = fmaf(wt, a[k * 32], T[k]);
+        }
+        const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+        const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+        const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+        if (n_ok) {
+          if (vertices) {
+            float* o = vertices + ((size_t)n * kV + gv) * 3;
+            o[0] = ox; o[1] = oy; o[2] = oz;
+          }
+          if (ci >= 0) {
+            float* o = w.vcompact + ((size_t)n * m.S + ci) * 3;
+            o[0] = ox; o[1] = oy; o[2] = oz;
+          }
+        }
       }
     }
   }
