@@ -274,6 +274,11 @@ struct glamr_opt {
   cudaEvent_t ev_lbs0, ev_lbs1;
   cudaEvent_t ev[24];         // timing == 2: one event after every launch of glamr_opt_backward / glamr_opt_apply
   int n_ev;
+  // glamr_opt_iterate: one captured iteration (backward + apply), valid for the arguments it was captured with
+  cudaStream_t cap_stream;
+  cudaGraphExec_t iter_exec;
+  const void* cap_theta; const void* cap_reduce; const void* cap_hist;
+  double cap_lr; int cap_stride; unsigned long long cap_gen, gen;   // gen advances with every glamr_opt_set_problem
 };
 
 extern "C" size_t glamr_sizeof_person(void) { return sizeof(glamr_person_t); }
@@ -373,6 +378,8 @@ extern "C" int glamr_opt_kernel_times(glamr_opt_t* st, float* ms, int* n) {
 }
 
 extern "C" int glamr_opt_destroy(glamr_opt_t* st) {
+  if (st && st->iter_exec) cudaGraphExecDestroy(st->iter_exec);
+  if (st && st->cap_stream) cudaStreamDestroy(st->cap_stream);
   if (!st) return GLAMR_OK;
   if (st->ev_lbs0) { cudaEventDestroy(st->ev_lbs0); cudaEventDestroy(st->ev_lbs1); for (int i = 0; i < 24; ++i) cudaEventDestroy(st->ev[i]); }
   cudaFree(st->arena);
@@ -384,6 +391,7 @@ extern "C" int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* pb,
   if (!st || !pb) return GLAMR_EINVAL;
   if (pb->P != st->pb.P || pb->T != st->pb.T || pb->J != st->pb.J || pb->n_params != st->pb.n_params) return GLAMR_EINVAL;
   st->pb = *pb;
+  st->gen++;
   compute_gs(st);
   if (reset_adam) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -472,6 +480,45 @@ extern "C" int glamr_opt_apply(glamr_opt_t* st, float* theta, const float* reduc
   apply_kernel<<<blocks < 296 ? blocks : 296, 256, 0, s>>>(c, theta, reduce_buf, lr, st->adam, loss_terms, loss_hist_stride, st->tickets + 1);
   GLAMR_LAUNCH_CHECK();
   GLAMR_MARK();
+  return GLAMR_OK;
+}
+
+extern "C" int glamr_opt_iterate(glamr_opt_t* st, float* theta, float* reduce_buf, double lr, float* loss_terms, int loss_hist_stride,
+                                 int n_iters, int use_graph, void* stream) {
+  if (!st || !theta || !reduce_buf || n_iters < 0) return GLAMR_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc, done = 0;
+  auto eager = [&](cudaStream_t q) -> int {
+    if ((rc = glamr_opt_backward(st, theta, reduce_buf, q))) return rc;
+    return glamr_opt_apply(st, theta, reduce_buf, lr, loss_terms, loss_hist_stride, q);
+  };
+  if (!use_graph || st->timing) {
+    for (; done < n_iters; ++done)
+      if ((rc = eager(s))) return rc;
+    return GLAMR_OK;
+  }
+  const bool valid = st->iter_exec && st->cap_gen == st->gen && st->cap_theta == theta && st->cap_reduce == reduce_buf &&
+                     st->cap_hist == loss_terms && st->cap_lr == lr && st->cap_stride == loss_hist_stride;
+  if (!valid) {
+    if (n_iters == 0) return GLAMR_OK;
+    if ((rc = eager(s))) return rc;          // first iteration eagerly: module loading / function attributes happen outside capture
+    done = 1;
+    if (n_iters == 1) return GLAMR_OK;
+    if (st->iter_exec) { cudaGraphExecDestroy(st->iter_exec); st->iter_exec = nullptr; }
+    if (!st->cap_stream) GLAMR_CUDA_TRY(cudaStreamCreateWithFlags(&st->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    GLAMR_CUDA_TRY(cudaStreamBeginCapture(st->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = eager(st->cap_stream);
+    const cudaError_t ce = cudaStreamEndCapture(st->cap_stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) return (int)ce;
+    const cudaError_t ie = cudaGraphInstantiate(&st->iter_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { st->iter_exec = nullptr; return (int)ie; }
+    st->cap_gen = st->gen; st->cap_theta = theta; st->cap_reduce = reduce_buf; st->cap_hist = loss_terms; st->cap_lr = lr;
+    st->cap_stride = loss_hist_stride;
+  }
+  for (; done < n_iters; ++done) GLAMR_CUDA_TRY(cudaGraphLaunch(st->iter_exec, s));
   return GLAMR_OK;
 }
 

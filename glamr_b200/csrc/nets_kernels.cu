@@ -113,14 +113,43 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
+__device__ int g_tc_dbg = 0;   // experiment switches (tools/tc_gemm_test.py, env GLAMR_TC_DEBUG); 0 in production
 constexpr int kTcThreads = 256;
 constexpr int kTcStages = 2;
 constexpr size_t kTcSmemBytesTotal = (size_t)kTcStages * 4 * kTcTileFloats * sizeof(float) + 64;
 
-// stage one 128x32 tile pair (X rows m0.., W rows n0.., K columns k0..k0+31) into shared memory as tf32 hi / lo
+// one K step (32 columns) of the 128-row X tile and the 128-row W tile, in flight in registers: 8 x 16 bytes per thread
+struct TcRegs {
+  float4 x[(TCM * TCK / 4) / kTcThreads], w[(TCM * TCK / 4) / kTcThreads];
+};
 template <bool VEC>
-__device__ __forceinline__ void tc_stage_tiles(float* st, int tid, int M, int N, int K, const float* __restrict__ X, int ldx,
-                                               const float* __restrict__ W, int m0, int n0, int k0) {
+__device__ __forceinline__ void tc_load_tiles(TcRegs& r, int tid, int M, int N, int K, const float* __restrict__ X, int ldx,
+                                              const float* __restrict__ W, int m0, int n0, int k0) {
+#pragma unroll
+  for (int i = 0; i < (TCM * TCK / 4) / kTcThreads; ++i) {
+    const int idx = tid + i * kTcThreads;
+    const int row = idx & 127, kg = idx >> 7;        // row, 16-byte K group (0..7)
+    const int k = k0 + kg * 4;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), wv = xv;
+    if (VEC) {
+      if (m0 + row < M && k < K) xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m0 + row) * ldx + k));
+      if (n0 + row < N && k < K) wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + row) * K + k));
+    } else {
+      float xa[4], wa[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        xa[q] = (m0 + row < M && k + q < K) ? X[(size_t)(m0 + row) * ldx + k + q] : 0.0f;
+        wa[q] = (n0 + row < N && k + q < K) ? W[(size_t)(n0 + row) * K + k + q] : 0.0f;
+      }
+      xv = make_float4(xa[0], xa[1], xa[2], xa[3]);
+      wv = make_float4(wa[0], wa[1], wa[2], wa[3]);
+    }
+    r.x[i] = xv;
+    r.w[i] = wv;
+  }
+}
+// split into tf32 hi / lo and store as K-major 8x16-byte core matrices (the layout umma_desc_kmajor_noswizzle describes)
+__device__ __forceinline__ void tc_store_tiles(float* st, int tid, const TcRegs& r) {
   float* Ahi = st;
   float* Alo = st + kTcTileFloats;
   float* Bhi = st + 2 * kTcTileFloats;
@@ -128,26 +157,12 @@ __device__ __forceinline__ void tc_stage_tiles(float* st, int tid, int M, int N,
 #pragma unroll
   for (int i = 0; i < (TCM * TCK / 4) / kTcThreads; ++i) {
     const int idx = tid + i * kTcThreads;
-    const int r = idx & 127, kg = idx >> 7;          // row, 16-byte K group (0..7)
-    const int k = k0 + kg * 4;
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), wv = xv;
-    if (VEC) {
-      if (m0 + r < M && k < K) xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * ldx + k));
-      if (n0 + r < N && k < K) wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * K + k));
-    } else {
-      float xa[4], wa[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        xa[q] = (m0 + r < M && k + q < K) ? X[(size_t)(m0 + r) * ldx + k + q] : 0.0f;
-        wa[q] = (n0 + r < N && k + q < K) ? W[(size_t)(n0 + r) * K + k + q] : 0.0f;
-      }
-      xv = make_float4(xa[0], xa[1], xa[2], xa[3]);
-      wv = make_float4(wa[0], wa[1], wa[2], wa[3]);
-    }
+    const int row = idx & 127, kg = idx >> 7;
+    const float4 xv = r.x[i], wv = r.w[i];
     float4 xh, xl, wh, wl;
     split_tf32(xv.x, xh.x, xl.x); split_tf32(xv.y, xh.y, xl.y); split_tf32(xv.z, xh.z, xl.z); split_tf32(xv.w, xh.w, xl.w);
     split_tf32(wv.x, wh.x, wl.x); split_tf32(wv.y, wh.y, wl.y); split_tf32(wv.z, wh.z, wl.z); split_tf32(wv.w, wh.w, wl.w);
-    const int off = (kg * TCM + r) * 4;
+    const int off = (kg * TCM + row) * 4;
     *reinterpret_cast<float4*>(Ahi + off) = xh;
     *reinterpret_cast<float4*>(Alo + off) = xl;
     *reinterpret_cast<float4*>(Bhi + off) = wh;
@@ -156,7 +171,8 @@ __device__ __forceinline__ void tc_stage_tiles(float* st, int tid, int M, int N,
 }
 
 // 256 threads; two shared-memory stages: while the tensor core works on stage s (12 UTCHMMA per K step, tracked by
-// tcgen05.commit -> mbarrier[s]) all threads fetch, split and store the next K step into stage s^1.
+// tcgen05.commit -> mbarrier[s]) all threads split and store K step it+1 into stage s^1 and already have the global
+// loads of step it+2 in flight in registers, so the L2 latency never sits on the critical path of these small GEMMs.
 template <int ACT, bool VEC>
 __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, int N, int K, const float* __restrict__ X, int ldx,
                                                                          const float* __restrict__ W, const float* __restrict__ bias,
@@ -177,7 +193,12 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
     mbar_init(&bar[1], 1);
     mbar_fence_init();
   }
-  tc_stage_tiles<VEC>(stage0, tid, M, N, K, X, ldx, W, m0, n0, 0);
+  const int nk = (K + TCK - 1) / TCK;
+  const int dbg = g_tc_dbg;
+  TcRegs regs;
+  tc_load_tiles<VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, 0);
+  tc_store_tiles(stage0, tid, regs);
+  if (nk > 1) tc_load_tiles<VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, TCK);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -186,13 +207,12 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
 
-  const int nk = (K + TCK - 1) / TCK;
   for (int it = 0; it < nk; ++it) {
     const int s = it & 1;
     float* st = stage0 + s * 4 * kTcTileFloats;
     if (tid == 0) {
 #pragma unroll
-      for (int k8 = 0; k8 < TCK / 8; ++k8) {           // one tf32 MMA consumes K = 8 (two 16-byte K groups)
+      for (int k8 = 0; k8 < ((dbg & 1) ? 0 : TCK / 8); ++k8) {           // one tf32 MMA consumes K = 8 (two 16-byte K groups)
         const size_t koff = (size_t)k8 * 2 * TCM * 4;   // floats
         const uint64_t dah = umma_desc_kmajor_noswizzle(st + koff), dal = umma_desc_kmajor_noswizzle(st + kTcTileFloats + koff);
         const uint64_t dbh = umma_desc_kmajor_noswizzle(st + 2 * kTcTileFloats + koff), dbl = umma_desc_kmajor_noswizzle(st + 3 * kTcTileFloats + koff);
@@ -206,7 +226,8 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
     if (it + 1 < nk) {
       // stage s^1 was consumed by the MMAs of step it-1: wait for their commit, then refill it while step `it` computes
       if (it >= 1) mbar_wait(&bar[s ^ 1], ((it - 1) >> 1) & 1);
-      tc_stage_tiles<VEC>(stage0 + (s ^ 1) * 4 * kTcTileFloats, tid, M, N, K, X, ldx, W, m0, n0, (it + 1) * TCK);
+      if (!(dbg & 2)) tc_store_tiles(stage0 + (s ^ 1) * 4 * kTcTileFloats, tid, regs);
+      if (it + 2 < nk && !(dbg & 8)) tc_load_tiles<VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, (it + 2) * TCK);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
     }
@@ -214,14 +235,15 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
   mbar_wait(&bar[(nk - 1) & 1], ((nk - 1) >> 1) & 1);      // all MMAs done: the accumulator is final
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---- epilogue: warps 0-3 own TMEM lanes (= rows) 32w..32w+31
-  if (warp < 4) {
-    const int m = m0 + warp * 32 + lane;
+  // ---- epilogue: a warp may read TMEM lanes (= rows) 32 (w % 4) .. +31; warps 0-3 take columns 0-63, warps 4-7 columns 64-127
+  if (!(dbg & 4)) {
+    const int wq = warp & 3, wh = warp >> 2;
+    const int m = m0 + wq * 32 + lane;
 #pragma unroll 1
-    for (int cc = 0; cc < TCN / 32; ++cc) {
+    for (int cc = wh * (TCN / 64); cc < (wh + 1) * (TCN / 64); ++cc) {
       if (n0 + cc * 32 >= N) break;
       uint32_t v[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32);
+      const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(cc * 32);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, "
@@ -232,7 +254,29 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
             "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < M) {
+      const int nb = n0 + cc * 32;
+      if (m < M && nb + 32 <= N && (ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+        float4* yrow = reinterpret_cast<float4*>(Y + (size_t)m * ldy + nb);          // this lane's 128 contiguous bytes
+        const bool bvec = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(bias2)) & 15) == 0 && (nb & 3) == 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+          if (bvec) {
+            if (bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + nb + j)); bsum[0] += t.x; bsum[1] += t.y; bsum[2] += t.z; bsum[3] += t.w; }
+            if (bias2) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias2 + nb + j)); bsum[0] += t.x; bsum[1] += t.y; bsum[2] += t.z; bsum[3] += t.w; }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bsum[q] = (bias ? __ldg(bias + nb + j + q) : 0.0f) + (bias2 ? __ldg(bias2 + nb + j + q) : 0.0f);
+          }
+          float o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            o[q] = __uint_as_float(v[j + q]) + bsum[q];
+            if (ACT == 1) o[q] = fmaxf(o[q], 0.0f);
+          }
+          yrow[j >> 2] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      } else if (m < M) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n0 + cc * 32 + j;
@@ -250,13 +294,24 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TCN));
 }
 
-static int g_gemm_mode = 1;   // 1 = tcgen05 3xTF32 (default), 0 = FP32 SIMT (kept for A/B verification)
+static int g_gemm_mode = 1;   // 1 = tcgen05 3xTF32 for the transformer (default), 0 = FP32 SIMT everywhere (A/B verification)
+// The trajectory predictor (MLP + LSTM, M = T*B rows, outputs integrated over T frames by the trajectory codec) stays on the
+// FP32 SIMT GEMM: its matrices are launch-latency sized and its per-frame heading error accumulates through the prefix sum.
+struct ScopedFp32Gemm {
+  int saved;
+  ScopedFp32Gemm() : saved(g_gemm_mode) { g_gemm_mode = 0; }
+  ~ScopedFp32Gemm() { g_gemm_mode = saved; }
+};
 
 static int gemm(cudaStream_t s, int M, int N, int K, const float* X, int ldx, const float* W, const float* b, const float* b2, float* Y,
                 int ldy, int act) {
   if (g_gemm_mode == 1) {
     static bool attr = false;
     if (!attr) {
+      if (const char* e = getenv("GLAMR_TC_DEBUG")) {
+        const int v = atoi(e);
+        GLAMR_CUDA_TRY(cudaMemcpyToSymbol(g_tc_dbg, &v, sizeof(int)));
+      }
       GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
       GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
       GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
@@ -740,6 +795,7 @@ extern "C" int glamr_trajpred_forward(const glamr_net* n, int T, int B, const fl
                                       float* out_orient_aa, float* workspace, size_t workspace_floats, void* stream) {
   if (!n || T <= 0 || B <= 0 || !in_joint_pos || !out_local_traj || !out_trans || !out_orient_aa || !workspace) return GLAMR_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
+  ScopedFp32Gemm fp32_only;
   int e = 0;
   const std::string ce = "context_encoder.", dd = "data_decoder.";
   const float* im0w = W(n, ce + "in_mlp.affine_layers.0.weight", 512 * 69, &e), * im0b = W(n, ce + "in_mlp.affine_layers.0.bias", 512, &e);

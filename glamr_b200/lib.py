@@ -101,6 +101,7 @@ def load():
     lib.glamr_sizeof_problem.restype = ctypes.c_size_t
     lib.glamr_opt_reduce_count.restype = ctypes.c_size_t
     lib.glamr_opt_apply.argtypes = [_vp, _vp, _vp, ctypes.c_double, _vp, ctypes.c_int, _vp]
+    lib.glamr_opt_iterate.argtypes = [_vp, _vp, _vp, ctypes.c_double, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
     if lib.glamr_sizeof_person() != ctypes.sizeof(Person) or lib.glamr_sizeof_problem() != ctypes.sizeof(Problem):
         raise GlamrError('struct layout mismatch between include/glamr_b200.h and glamr_b200/lib.py')
     _lib = lib

@@ -101,7 +101,9 @@ class MotionInfillerVAE:
                 kp = torch.ones((B, WINDOW), dtype=torch.uint8, device=dev)
                 kp[:, :eb - s] = key_pad_all[:, s:eb].to(torch.uint8)
                 kp[:, :PAST] = 0
-                if latent is not None:
+                if latent is not None and latent.dim() == 3:                 # [B, windows, nz]: one latent per sequence
+                    eps, rows = latent[:, i].to(dev, torch.float32).repeat_interleave(sample_num, dim=0).contiguous(), B
+                elif latent is not None:
                     eps, rows = latent[[i]].to(dev, torch.float32).contiguous(), 1
                 else:
                     eps, rows = torch.randn((B, NZ), device=dev), B
@@ -182,6 +184,7 @@ def _find_checkpoint(cfg_dir, cp='best'):
 
 
 class MotionTrajJointModel:
+    supports_person_batch = True     # inference() accepts [B, T, 69] with B > 1 (GlobalReconOptimizer.infer_motion_traj_all)
 
     def __init__(self, cfg=None, device=torch.device('cuda'), log=None, smpl=None, states=None):
         """cfg: config id / object of the joint model (only its checkpoint locations are used).  states: optional

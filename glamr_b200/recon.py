@@ -13,7 +13,6 @@ import time
 import numpy as np
 import torch
 from scipy.interpolate import interp1d
-from scipy.spatial.transform import Rotation
 
 from . import geometry as G
 from . import lib as L
@@ -46,6 +45,42 @@ def tensor_to_numpy(x):
     if isinstance(x, (list, tuple)):
         return type(x)(tensor_to_numpy(v) for v in x)
     return x
+
+
+def rotmats_to_rotvec(mats):
+    """``Rotation.from_matrix(mats).as_rotvec()`` (global_recon_model.py:106-107) as vectorised numpy, float64.
+
+    SciPy projects every float32-accurate input onto SO(3) with one SVD per matrix (12 ms for a 300-frame track); the
+    same polar factor U V^T is reached here by two Newton steps R <- (R + R^-T) / 2 written with cross products, then
+    the usual largest-diagonal quaternion branch and the rotation-vector scaling (series below 1e-3 rad)."""
+    R = np.asarray(mats, dtype=np.float64).reshape(-1, 3, 3)
+    for _ in range(2):
+        c = np.stack([np.cross(R[:, 1], R[:, 2]), np.cross(R[:, 2], R[:, 0]), np.cross(R[:, 0], R[:, 1])], axis=1)   # cofactors
+        det = np.einsum('ni,ni->n', R[:, 0], c[:, 0])
+        R = 0.5 * (R + c / det[:, None, None])
+    d = np.stack([R[:, 0, 0], R[:, 1, 1], R[:, 2, 2], R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]], axis=1)
+    choice = d.argmax(axis=1)
+    q = np.empty((R.shape[0], 4))
+    for i in range(3):
+        sel = np.where(choice == i)[0]
+        j, k = (i + 1) % 3, (i + 2) % 3
+        q[sel, i] = 1 - d[sel, 3] + 2 * R[sel, i, i]
+        q[sel, j] = R[sel, j, i] + R[sel, i, j]
+        q[sel, k] = R[sel, k, i] + R[sel, i, k]
+        q[sel, 3] = R[sel, k, j] - R[sel, j, k]
+    sel = np.where(choice == 3)[0]
+    q[sel, 0] = R[sel, 2, 1] - R[sel, 1, 2]
+    q[sel, 1] = R[sel, 0, 2] - R[sel, 2, 0]
+    q[sel, 2] = R[sel, 1, 0] - R[sel, 0, 1]
+    q[sel, 3] = 1 + d[sel, 3]
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[q[:, 3] < 0] *= -1
+    angle = 2 * np.arctan2(np.linalg.norm(q[:, :3], axis=1), q[:, 3])
+    small = angle <= 1e-3
+    a2 = angle * angle
+    with np.errstate(divide='ignore', invalid='ignore'):
+        scale = np.where(small, 2 + a2 / 12 + 7 * a2 * a2 / 2880, angle / np.sin(angle / 2))
+    return scale[:, None] * q[:, :3]
 
 
 def _sec_to_time(secs):
@@ -140,7 +175,7 @@ class GlobalReconOptimizer:
         d['scale'] = None
         rotmats = est['smpl_pose_quat_wroot']
         nv = rotmats.shape[0]
-        aa = Rotation.from_matrix(rotmats.reshape(-1, 3, 3)).as_rotvec().reshape(nv, -1, 3).astype(np.float32)
+        aa = rotmats_to_rotvec(rotmats).reshape(nv, -1, 3).astype(np.float32)
         d['smpl_pose'] = aa[:, 1:].reshape(-1, 69)
         if gt_entry is not None:
             d['smpl_pose_gt'] = gt_entry['pose'][:, 3:]
@@ -191,20 +226,43 @@ class GlobalReconOptimizer:
         ex = d['exist_frames']
         batch = {'in_body_pose': d['smpl_pose_nofill'][ex].unsqueeze(0).clone(), 'frame_mask': d['visible'][ex].unsqueeze(0).clone()}
         out = self.mt_model.inference(batch, sample_num=1)
+        self._take_prior_output(d, out, 0)
+
+    def infer_motion_traj_all(self, persons):
+        """The reference runs the learned prior once per person with batch size 1 (:230-232 -> :353-392).  When every
+        person exists for the same number of frames and the prior object declares `supports_person_batch`, the persons
+        form one batch [P, T, 69] instead: same per-person arithmetic, P times fewer launches."""
+        if self.mt_model is None:
+            return
+        ds = list(persons.values())
+        lens = {int(d['exist_len']) for d in ds}
+        if len(ds) > 1 and len(lens) == 1 and getattr(self.mt_model, 'supports_person_batch', False):
+            batch = {'in_body_pose': torch.stack([d['smpl_pose_nofill'][d['exist_frames']] for d in ds]),
+                     'frame_mask': torch.stack([d['visible'][d['exist_frames']] for d in ds])}
+            out = self.mt_model.inference(batch, sample_num=1)
+            for b, d in enumerate(ds):
+                self._take_prior_output(d, out, b)
+        else:
+            for d in ds:
+                self.infer_motion_traj(d)
+
+    def _take_prior_output(self, d, out, b):
+        """:368-392 for batch row b of the prior's output"""
+        ex = d['exist_frames']
         if self.flag_infill_motion:
             d['infilled'] = True
             d['smpl_pose'] = d['smpl_pose'].detach().clone()
-            d['smpl_pose'][ex] = out['infer_out_body_pose'][0, 0].to(d['smpl_pose'])
+            d['smpl_pose'][ex] = out['infer_out_body_pose'][b, 0].to(d['smpl_pose'])
         if self.flag_pred_traj:
             d['traj_predicted'] = True
-            d['traj_local_pred'] = out['infer_out_local_traj_tp'][:, 0, 0, :].clone().float()
+            d['traj_local_pred'] = out['infer_out_local_traj_tp'][:, b, 0, :].clone().float()
             d['smpl_orient_world_base'] = d['smpl_orient_world_base'].detach().clone()
             d['root_trans_world_base'] = d['root_trans_world_base'].detach().clone()
             if 'infer_out_pose' in out:
-                d['smpl_orient_world_base'][ex] = out['infer_out_pose'][0, 0, :, :3].to(d['smpl_orient_world_base'])
+                d['smpl_orient_world_base'][ex] = out['infer_out_pose'][b, 0, :, :3].to(d['smpl_orient_world_base'])
             if 'infer_out_orient' in out:
-                d['smpl_orient_world_base'][ex] = out['infer_out_orient'][0, 0].to(d['smpl_orient_world_base'])
-            d['root_trans_world_base'][ex] = out['infer_out_trans'][0, 0].to(d['root_trans_world_base'])
+                d['smpl_orient_world_base'][ex] = out['infer_out_orient'][b, 0].to(d['smpl_orient_world_base'])
+            d['root_trans_world_base'][ex] = out['infer_out_trans'][b, 0].to(d['root_trans_world_base'])
             d['smpl_orient_world'] = d['smpl_orient_world_base']
             d['root_trans_world'] = d['root_trans_world_base']
 
@@ -322,8 +380,7 @@ class GlobalReconOptimizer:
             d['smpl_pose_nofill'][~d['exist_frames']] = 0.0
             persons[idx] = d
         if self.flag_infer_motion_traj:
-            for d in persons.values():
-                self.infer_motion_traj(d)
+            self.infer_motion_traj_all(persons)
         if not (self.flag_infer_motion_traj and self.flag_pred_traj):
             raise NotImplementedError('flag_pred_traj=false (default trajectory) is not implemented in the CUDA path')
         for d in persons.values():
@@ -477,33 +534,43 @@ class GlobalReconOptimizer:
             done = 0
             t_stage = time.time()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if opt_niters > 0:
+            native = self.world == 1                             # no reduction between backward and apply: the library owns the loop
+            if native and opt_niters > 0:
+                L.check(lib.glamr_opt_iterate(self._opt, L.ptr(self._theta), L.ptr(self._reduce), float(opt_lr), L.ptr(hist), NUM_TERMS + 1,
+                                              1, int(self.use_cuda_graph), L.stream_ptr()), 'glamr_opt_iterate')
+                done = 1
+            elif opt_niters > 0:
                 one_iteration()                                  # warm-up (also sets kernel attributes) = iteration 0
                 done = 1
                 if self.use_cuda_graph and opt_niters > 2:
-                    try:                                         # NCCL all-reduce is capturable too (world > 1)
+                    try:                                         # the NCCL all-reduce is capturable too
                         graph = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(graph):
                             one_iteration()
                     except Exception as e:                       # capture is an optimisation, eager launches are equivalent
-                        if self.world == 1:
-                            raise
                         graph = None
                         torch.cuda.synchronize()
                         if self.log is not None:
                             self.log.info(f'CUDA-graph capture with NCCL unavailable ({e}); running eager iterations')
             ev0.record()
             chunk = max(int(self.log_interval), 1)
+            logging_on = self.log is not None or self.specs.get('print_logs', False)
+            if native and not logging_on:
+                chunk = max(opt_niters, 1)
             logged = 0
             while done < opt_niters:
                 todo = min(chunk, opt_niters - done)
-                for _ in range(todo):
-                    if graph is not None:
-                        graph.replay()
-                    else:
-                        one_iteration()
+                if native:
+                    L.check(lib.glamr_opt_iterate(self._opt, L.ptr(self._theta), L.ptr(self._reduce), float(opt_lr), L.ptr(hist), NUM_TERMS + 1,
+                                                  todo, int(self.use_cuda_graph), L.stream_ptr()), 'glamr_opt_iterate')
+                else:
+                    for _ in range(todo):
+                        if graph is not None:
+                            graph.replay()
+                        else:
+                            one_iteration()
                 done += todo
-                if self.log is not None or self.specs.get('print_logs', False):
+                if logging_on:
                     logged = self._write_logs(hist, logged, done, opt_niters, opt_lr, loss_cfg, stage, data['seq_name'], t_stage)
             ev1.record()
             ev1.synchronize()

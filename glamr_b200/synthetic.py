@@ -181,13 +181,23 @@ class LatentInjector:
     def __init__(self, model, seed=0):
         self.model, self.seed, self.calls = model, seed, 0
 
+    @property
+    def supports_person_batch(self):
+        return getattr(self.model, 'supports_person_batch', False)
+
     def inference(self, batch, sample_num=1):
         import torch
-        T = batch['in_body_pose'].shape[1]
-        g = torch.Generator().manual_seed(self.seed + 101 * self.calls)
-        self.calls += 1
-        b = dict(batch)
+        B, T = batch['in_body_pose'].shape[:2]
         dev = batch['in_body_pose'].device
-        b['in_motion_latent'] = torch.randn(int(np.ceil((T - 10) / 30)), 128, generator=g).to(dev)
-        b['in_traj_latent'] = torch.randn(1, 128, generator=g).to(dev)
+        zm, zt = [], []
+        for _ in range(B):                       # sequence b of a batched call draws what the b-th single call would have
+            g = torch.Generator().manual_seed(self.seed + 101 * self.calls)
+            self.calls += 1
+            zm.append(torch.randn(int(np.ceil((T - 10) / 30)), 128, generator=g))
+            zt.append(torch.randn(1, 128, generator=g))
+        b = dict(batch)
+        if B == 1:
+            b['in_motion_latent'], b['in_traj_latent'] = zm[0].to(dev), zt[0].to(dev)
+        else:
+            b['in_motion_latent'], b['in_traj_latent'] = torch.stack(zm).to(dev), torch.cat(zt).to(dev)
         return self.model.inference(b, sample_num=sample_num)

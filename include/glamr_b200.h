@@ -219,6 +219,12 @@ int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* reduce_buf, v
  * written at loss_terms + k * loss_hist_stride, so a replayed graph fills a per-iteration history. */
 int glamr_opt_apply(glamr_opt_t* st, float* theta, const float* reduce_buf, double lr, float* loss_terms,
                     int loss_hist_stride, void* stream);
+/* n_iters x (glamr_opt_backward + glamr_opt_apply) for a single-rank job (no reduction between the two).  With
+ * use_graph != 0 the iteration is captured once into a CUDA graph owned by the handle (re-captured when the problem
+ * or any argument changes) and replayed: the loop `for _ in range(opt_niters): optimizer.step(closure)` of
+ * global_recon_model.py:558-569 becomes opt_niters graph launches with no host work in between. */
+int glamr_opt_iterate(glamr_opt_t* st, float* theta, float* reduce_buf, double lr, float* loss_terms, int loss_hist_stride,
+                      int n_iters, int use_graph, void* stream);
 /* loss_terms only, no update (GlobalReconOptimizer.compute_loss, :533-545) */
 int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms, void* stream);
 

@@ -20,11 +20,15 @@ class ReplayMT:
     def __init__(self, gold, device='cpu'):
         self.gold, self.calls, self.device = gold, 0, device
 
+    supports_person_batch = True
+
     def inference(self, batch, sample_num=1):
-        i = self.calls
-        self.calls += 1
-        return {k: torch.tensor(self.gold[f'mt/{i}/{k}'], device=self.device) for k in
-                ['infer_out_body_pose', 'infer_out_local_traj_tp', 'infer_out_orient', 'infer_out_trans']}
+        B = batch['in_body_pose'].shape[0]           # a batched call over persons consumes B consecutive recorded calls
+        cat_dim = {'infer_out_body_pose': 0, 'infer_out_local_traj_tp': 1, 'infer_out_orient': 0, 'infer_out_trans': 0}
+        out = {k: torch.cat([torch.tensor(self.gold[f'mt/{self.calls + b}/{k}'], device=self.device) for b in range(B)], dim=d)
+               for k, d in cat_dim.items()}
+        self.calls += B
+        return out
 
 
 def case_setup(name, smpl_assets):

@@ -1,6 +1,7 @@
 """CPU-only checks: the C-ABI library exports every symbol include/glamr_b200.h declares (no compute calls), struct
 layouts agree with the ctypes mirror, the built-in stage tables equal the reference YAML, the product refuses CPU."""
 import ctypes
+import numpy as np
 import os
 
 import pytest
@@ -60,3 +61,15 @@ def test_config_surface():
     cfg = Config('glamr_static_multi', out_dir='/tmp/glamr_b200_cfg_test')
     assert cfg.id == 'glamr_static_multi' and cfg.grecon_model_name == 'global_recon_model'
     assert list(cfg.opt_stage_specs) == ['init_opt', 'main_opt'] and cfg.grecon_model_specs['flag_fixed_cam'] is True
+
+
+def test_rotmats_to_rotvec_matches_scipy():
+    """host step of init_data (global_recon_model.py:106-107): float32 rotation matrices -> rotation vectors"""
+    from scipy.spatial.transform import Rotation
+    from glamr_b200.recon import rotmats_to_rotvec
+    rng = np.random.default_rng(0)
+    rv = rng.normal(size=(4000, 3)) * rng.uniform(0, 1.5, size=(4000, 1))
+    rv[:50] *= 1e-5                                                                       # series branch
+    rv[50:100] = rv[50:100] / np.linalg.norm(rv[50:100], axis=1, keepdims=True) * (np.pi - 1e-4)   # near pi
+    mats = Rotation.from_rotvec(rv).as_matrix().astype(np.float32)                        # float32-accurate, as HybrIK stores them
+    np.testing.assert_allclose(rotmats_to_rotvec(mats), Rotation.from_matrix(mats).as_rotvec(), atol=1e-10)
