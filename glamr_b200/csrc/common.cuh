@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/glamr_b200.h"
 
@@ -42,6 +43,10 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// raise the pending transaction count without arriving (the arrival comes later with mbar_expect_tx)
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -65,6 +70,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
+// ---- programmatic dependent launch (PDL): every kernel of the optimiser iteration is launched with the
+// programmatic-stream-serialization attribute, lets the next kernel be scheduled early (launch_dependents) and
+// waits for the previous grid's results (wait) only where it first touches them.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -75,5 +86,34 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+#if defined(__CUDACC__)
+// GLAMR_PDL = bit mask of the kernels launched with the attribute (A/B runs): 1 traj/cam forward, 2 pose_prep, 4 lbs,
+// 8 residuals, 16 traj/cam backward (+ mode-3 camera kernels), 32 apply
+constexpr int kPdlDefaultMask = 0;
+inline bool pdl_enabled(int bit) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("GLAMR_PDL");
+    mask = e ? atoi(e) : kPdlDefaultMask;
+  }
+  return (mask & bit) != 0;
+}
+// kernel<<<grid, block, smem, s>>>(args...) with the PDL attribute (GLAMR_PDL=0 falls back to a plain launch for A/B runs)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int bit, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(bit) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 }  // namespace glamr

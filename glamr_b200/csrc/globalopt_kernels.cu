@@ -53,6 +53,10 @@ __device__ bool grid_last_block(unsigned int* ticket) {
 // blocks [0,P): trajectory codec of one person; blocks [P, P+cam_blocks): camera of 256 frames each (modes 0-2)
 __global__ void __launch_bounds__(kScanThreads) traj_cam_forward_kernel(OptCtx c, int with_cam) {
   __shared__ float sm[kScanThreads / 32 + 1];
+  pdl_launch_dependents();
+  pdl_wait();
+  // [grad | term sums] of this iteration start from zero (the previous iteration's apply has consumed them)
+  for (int i = blockIdx.x * kScanThreads + threadIdx.x; i < c.pb.n_params + GLAMR_NUM_TERMS; i += gridDim.x * kScanThreads) c.sc.grad[i] = 0.0f;
   if ((int)blockIdx.x >= c.pb.P) {
     const int t = (blockIdx.x - c.pb.P) * kScanThreads + threadIdx.x;
     if (with_cam && t < c.pb.T) cam_forward(c, t);
@@ -75,6 +79,8 @@ __global__ void __launch_bounds__(kScanThreads) traj_cam_forward_kernel(OptCtx c
 }
 
 __global__ void __launch_bounds__(kFrameThreads) cam_forward_kernel(OptCtx c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < c.pb.T) cam_forward(c, t);
 }
@@ -83,6 +89,8 @@ __global__ void __launch_bounds__(kFrameThreads) cam_forward_kernel(OptCtx c) {
 // reprojection terms, warp-shuffle sums, then lane 0 finishes the per-frame terms.  4 frame-persons per CTA.
 __global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c, SmplDev m, SmplWorkspace wo, int n_begin, double* partial) {
   __shared__ double sm[(kFrameThreads / 32) * GLAMR_NUM_TERMS];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n = blockIdx.x * (kFrameThreads / 32) + wid;
   const int N = c.pb.P * c.pb.T, J = c.pb.J;
@@ -135,6 +143,8 @@ __global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c
 
 __global__ void __launch_bounds__(kFrameThreads) camera_backward_kernel(OptCtx c, double* partial) {
   __shared__ double sm[(kFrameThreads / 32) * GLAMR_NUM_TERMS];
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   TermAcc acc;
   acc.clear();
@@ -143,6 +153,8 @@ __global__ void __launch_bounds__(kFrameThreads) camera_backward_kernel(OptCtx c
 }
 
 __global__ void __launch_bounds__(kFrameThreads) camera_scatter_kernel(OptCtx c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < c.pb.T) camera_scatter_to_persons(c, s);
 }
@@ -180,6 +192,8 @@ __global__ void __launch_bounds__(kScanThreads) traj_cam_backward_kernel(OptCtx 
                                                                          int n_slots, float* reduce_buf, unsigned int* ticket) {
   __shared__ float sm[kScanThreads / 32 + 1];
   __shared__ double smd[(kScanThreads / 32) * GLAMR_NUM_TERMS];
+  pdl_launch_dependents();
+  pdl_wait();
   TermAcc acc;
   acc.clear();
   if ((int)blockIdx.x >= c.pb.P) {
@@ -231,6 +245,8 @@ __global__ void __launch_bounds__(32) losses_kernel(OptCtx c, const float* __res
 // loss terms (block 0) + torch.optim.Adam step; the last CTA to finish advances the step count / beta powers
 __global__ void __launch_bounds__(256) apply_kernel(OptCtx c, float* __restrict__ theta, const float* __restrict__ reduce_buf, double lr,
                                                     AdamState ad, float* loss_terms, int hist_stride, unsigned int* ticket) {
+  pdl_launch_dependents();
+  pdl_wait();
   const double b1 = ad.beta_pow[0] * 0.9, b2 = ad.beta_pow[1] * 0.999, step = ad.beta_pow[2];
   if (blockIdx.x == 0 && threadIdx.x == 0 && loss_terms) write_losses(c, reduce_buf, loss_terms + (hist_stride > 0 ? (size_t)step * hist_stride : 0));
   const float bc2s = (float)sqrt(1.0 - b2);
@@ -415,14 +431,11 @@ extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* re
   const glamr_problem_t& pb = st->pb;
   const int N = pb.P * pb.T;
   OptCtx c = make_ctx(st, theta, reduce_buf);
-  GLAMR_CUDA_TRY(cudaMemsetAsync(reduce_buf, 0, sizeof(float) * ((size_t)pb.n_params + GLAMR_NUM_TERMS), s));
   const bool from_persons = pb.cam_mode == GLAMR_CAM_FROM_PERSONS;
-  traj_cam_forward_kernel<<<pb.P + st->cam_blocks, kScanThreads, 0, s>>>(c, from_persons ? 0 : 1);
-  GLAMR_LAUNCH_CHECK();
+  GLAMR_CUDA_TRY(launch_pdl(1, traj_cam_forward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1));   // also zeroes reduce_buf
   GLAMR_MARK();
   if (from_persons) {          // the camera is the mean of the persons' world transforms: needs traj_forward of all persons
-    cam_forward_kernel<<<st->slots_cam, kFrameThreads, 0, s>>>(c);
-    GLAMR_LAUNCH_CHECK();
+    GLAMR_CUDA_TRY(launch_pdl(1, cam_forward_kernel, dim3(st->slots_cam), dim3(kFrameThreads), 0, s, c));
   }
   GLAMR_MARK();
   // SMPL for the persons this rank owns (global_recon_model.py:517-524); tile-major scratch (A, pf) is local to the launch
@@ -435,30 +448,26 @@ extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* re
     const int nn = n_end - n_begin;
     int rc;
     if ((rc = launch_pose_prep(st->smpl, nn, st->sc.orient_world + (size_t)n_begin * 3, pb.smpl_pose_all + (size_t)n_begin * 69,
-                               pb.smpl_beta_all + (size_t)n_begin * kNB, 1, wo, s))) return rc;
+                               pb.smpl_beta_all + (size_t)n_begin * kNB, 1, wo, s, true))) return rc;
     GLAMR_MARK();
     if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
-    if ((rc = launch_lbs(st->smpl, 0, nn, pb.smpl_beta_all + (size_t)n_begin * kNB, wo, nullptr, s))) return rc;
+    if ((rc = launch_lbs(st->smpl, 0, nn, pb.smpl_beta_all + (size_t)n_begin * kNB, wo, nullptr, s, true))) return rc;
     if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
     GLAMR_MARK();
   }
   double* part_res = st->partial;
   double* part_traj = st->partial + (size_t)st->slots_res * GLAMR_NUM_TERMS;
   double* part_cam3 = part_traj + (size_t)(pb.P + st->cam_blocks) * GLAMR_NUM_TERMS;
-  frame_residuals_kernel<<<st->slots_res, kFrameThreads, 0, s>>>(c, st->smpl, wo, n_begin, part_res);
-  GLAMR_LAUNCH_CHECK();
+  GLAMR_CUDA_TRY(launch_pdl(8, frame_residuals_kernel, dim3(st->slots_res), dim3(kFrameThreads), 0, s, c, st->smpl, wo, n_begin, part_res));
   GLAMR_MARK();
   if (from_persons) {
-    camera_backward_kernel<<<st->slots_cam, kFrameThreads, 0, s>>>(c, part_cam3);
-    GLAMR_LAUNCH_CHECK();
-    camera_scatter_kernel<<<st->slots_cam, kFrameThreads, 0, s>>>(c);
-    GLAMR_LAUNCH_CHECK();
+    GLAMR_CUDA_TRY(launch_pdl(16, camera_backward_kernel, dim3(st->slots_cam), dim3(kFrameThreads), 0, s, c, part_cam3));
+    GLAMR_CUDA_TRY(launch_pdl(16, camera_scatter_kernel, dim3(st->slots_cam), dim3(kFrameThreads), 0, s, c));
     GLAMR_MARK();
   }
   const int n_slots = st->slots_res + pb.P + st->cam_blocks + (from_persons ? st->slots_cam : 0);
-  traj_cam_backward_kernel<<<pb.P + st->cam_blocks, kScanThreads, 0, s>>>(c, from_persons ? 0 : 1, part_traj, st->partial, n_slots, reduce_buf,
-                                                                         st->tickets);
-  GLAMR_LAUNCH_CHECK();
+  GLAMR_CUDA_TRY(launch_pdl(16, traj_cam_backward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1, part_traj,
+                            (const double*)st->partial, n_slots, reduce_buf, st->tickets));
   GLAMR_MARK();
   return GLAMR_OK;
 }
@@ -477,8 +486,8 @@ extern "C" int glamr_opt_apply(glamr_opt_t* st, float* theta, const float* reduc
   cudaStream_t s = (cudaStream_t)stream;
   OptCtx c = make_ctx(st, theta, nullptr);
   const int blocks = (st->pb.n_params + 255) / 256;
-  apply_kernel<<<blocks < 296 ? blocks : 296, 256, 0, s>>>(c, theta, reduce_buf, lr, st->adam, loss_terms, loss_hist_stride, st->tickets + 1);
-  GLAMR_LAUNCH_CHECK();
+  GLAMR_CUDA_TRY(launch_pdl(32, apply_kernel, dim3(blocks < 296 ? blocks : 296), dim3(256), 0, s, c, theta, reduce_buf, lr, st->adam, loss_terms,
+                            loss_hist_stride, st->tickets + 1));
   GLAMR_MARK();
   return GLAMR_OK;
 }

@@ -21,6 +21,8 @@ namespace glamr {
 __global__ void __launch_bounds__(128) pose_prep_kernel(SmplDev m, int n, const float* __restrict__ orient,
                                                         const float* __restrict__ body_pose,
                                                         const float* __restrict__ betas, int use_betas, SmplWorkspace w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (f >= n) return;
@@ -148,6 +150,7 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
   const float* pd_slab = m.pd_tiles + (size_t)vtile * kPF * kTileCols;
   const float* pf_slab = w.pf + (size_t)(f0 >> 5) * kNChunks * kPfChunkFloats;
 
+  pdl_launch_dependents();
   // issue the per-vertex constant loads first: their latency overlaps the barrier set-up and the first TMA round trip
   float sdv[kVertsPerThread][30], vt[kVertsPerThread][3];
   {
@@ -188,11 +191,14 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
     tma_bulk_g2s(PDs + s * kChunkFloats, pd_slab + (size_t)c * kChunkFloats, kChunkBytes, &full[s]);
     tma_bulk_g2s(pfs + s * kPfChunkFloats, pf_slab + (size_t)c * kPfChunkFloats, kPfChunkBytes, &full[s]);
   };
+  // posedirs is a model constant: the first stages' slabs are fetched before this grid waits for its producer
+  // (pose_prep_kernel, PDL); their pose-feature halves and the A tile follow after pdl_wait().
   if (tid == 0) {
-    mbar_expect_tx(abar, (uint32_t)kATileFloats * sizeof(float));
-    tma_bulk_g2s(As, w.A + (size_t)(f0 >> 5) * kATileFloats, (uint32_t)kATileFloats * sizeof(float), abar);
 #pragma unroll
-    for (int c = 0; c < kStages - 1; ++c) issue_chunk(c);
+    for (int c = 0; c < kStages - 1; ++c) {
+      mbar_expect_tx_only(&full[c], kChunkBytes);
+      tma_bulk_g2s(PDs + c * kChunkFloats, pd_slab + (size_t)c * kChunkFloats, kChunkBytes, &full[c]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < (kFramesPerCta * kNB + kLbsThreads - 1) / kLbsThreads; ++i) {
@@ -218,6 +224,17 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
         a2 = fmaf(sdv[v][20 + l], bl[l], a2);
       }
       acc[f][3 * v + 0] = a0; acc[f][3 * v + 1] = a1; acc[f][3 * v + 2] = a2;
+    }
+  }
+
+  pdl_wait();                          // A and pf below are written by pose_prep_kernel
+  if (tid == 0) {
+    mbar_expect_tx(abar, (uint32_t)kATileFloats * sizeof(float));
+    tma_bulk_g2s(As, w.A + (size_t)(f0 >> 5) * kATileFloats, (uint32_t)kATileFloats * sizeof(float), abar);
+#pragma unroll
+    for (int c = 0; c < kStages - 1; ++c) {
+      mbar_expect_tx(&full[c], kPfChunkBytes);
+      tma_bulk_g2s(pfs + c * kPfChunkFloats, pf_slab + (size_t)c * kPfChunkFloats, kPfChunkBytes, &full[c]);
     }
   }
 
@@ -403,15 +420,22 @@ __global__ void fk24_finalize_kernel(int n, const float* __restrict__ jposed, co
 
 // ------------------------------------------------------------------------------------------------ launches
 int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* body_pose, const float* betas, int use_betas,
-                     const SmplWorkspace& w, cudaStream_t s) {
+                     const SmplWorkspace& w, cudaStream_t s, bool pdl) {
   if (n <= 0) return GLAMR_OK;
   const int blocks = (n + 3) / 4;
+  if (pdl) {
+    GLAMR_CUDA_TRY(launch_pdl(2, pose_prep_kernel, dim3(blocks), dim3(128), 0, s, m, n, orient, body_pose, betas, use_betas, w));
+    return GLAMR_OK;
+  }
   pose_prep_kernel<<<blocks, 128, 0, s>>>(m, n, orient, body_pose, betas, use_betas, w);
   GLAMR_LAUNCH_CHECK();
   return GLAMR_OK;
 }
 
-int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices, cudaStream_t s) {
+// pdl: launch with the programmatic-serialization attribute.  Only for callers whose betas are long-lived constants
+// (the optimiser): the kernel reads betas / shapedirs / posedirs BEFORE it waits for the preceding grid.
+int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices, cudaStream_t s,
+               bool pdl) {
   if (n_end <= n_begin) return GLAMR_OK;
   if (n_begin % kFramesPerCta != 0) return GLAMR_EINVAL;   // the tile-major scratch is indexed by whole frame tiles
   dim3 grid(kNVTiles, (n_end - n_begin + kFramesPerCta - 1) / kFramesPerCta);
@@ -425,14 +449,18 @@ int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, con
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbs_smem_bytes(3)));
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbs_smem_bytes(4)));
   }
-  if (m.K == 4 && stages == 4)
-    lbs_kernel<4, 4><<<grid, kLbsThreads, lbs_smem_bytes(4), s>>>(m, n_begin, n_end, betas, w, vertices, dbg);
-  else if (m.K == 4)
-    lbs_kernel<4, 3><<<grid, kLbsThreads, lbs_smem_bytes(3), s>>>(m, n_begin, n_end, betas, w, vertices, dbg);
-  else
-    lbs_kernel<0, 3><<<grid, kLbsThreads, lbs_smem_bytes(3), s>>>(m, n_begin, n_end, betas, w, vertices, dbg);
-  GLAMR_LAUNCH_CHECK();
-  return GLAMR_OK;
+  auto go = [&](auto kernel, size_t smem) -> int {
+    if (pdl) {
+      GLAMR_CUDA_TRY(launch_pdl(4, kernel, grid, dim3(kLbsThreads), smem, s, m, n_begin, n_end, betas, w, vertices, dbg));
+    } else {
+      kernel<<<grid, kLbsThreads, smem, s>>>(m, n_begin, n_end, betas, w, vertices, dbg);
+      GLAMR_LAUNCH_CHECK();
+    }
+    return GLAMR_OK;
+  };
+  if (m.K == 4 && stages == 4) return go(lbs_kernel<4, 4>, lbs_smem_bytes(4));
+  if (m.K == 4) return go(lbs_kernel<4, 3>, lbs_smem_bytes(3));
+  return go(lbs_kernel<0, 3>, lbs_smem_bytes(3));
 }
 
 int launch_joints_finalize(const SmplDev& m, int n, int orig_joints, const float* root_trans, const float* root_scale,

@@ -78,10 +78,10 @@ __device__ __forceinline__ void raw_joint(const SmplDev& m, const SmplWorkspace&
 // launches (smpl_kernels.cu); all asynchronous on `s`
 // orient may be NULL (zeros).  use_betas == 0 -> rest joints from the template only (SMPL.get_joints).
 int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* body_pose, const float* betas,
-                     int use_betas, const SmplWorkspace& w, cudaStream_t s);
+                     int use_betas, const SmplWorkspace& w, cudaStream_t s, bool pdl = false);
 // n_begin..n_end: frame-person range to skin.  vertices may be NULL.
 int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices,
-               cudaStream_t s);
+               cudaStream_t s, bool pdl = false);
 int launch_joints_finalize(const SmplDev& m, int n, int orig_joints, const float* root_trans, const float* root_scale,
                            const SmplWorkspace& w, float* joints, cudaStream_t s);
 int launch_reroot_vertices(int n, const float* root_raw, const float* root_trans, const float* root_scale,
