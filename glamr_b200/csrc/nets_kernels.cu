@@ -85,15 +85,16 @@ __global__ void __launch_bounds__(256) gemm_bias_act_kernel(int M, int N, int K,
 // the async proxy with fence.proxy.async, multiplied by one elected thread (12 MMAs per K step), completion tracked with
 // tcgen05.commit -> mbarrier; the epilogue reads the 128x128 fp32 accumulator with tcgen05.ld (32x32b.x32), adds the
 // bias, applies the activation and stores.
-constexpr int TCM = 128, TCN = 128, TCK = 32;
-constexpr int kTcTileFloats = TCM * TCK;                       // 4096 floats = 16 KB per operand tile
+constexpr int TCM = 128, TCK = 32;                              // N tile (NT) is a template parameter: 128, or 32 for one-tile-high problems
+constexpr int kTcATileFloats = TCM * TCK;                       // 4096 floats = 16 KB (hi or lo of the X tile)
 
-__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(const void* smem_ptr) {
+// rows = rows of the operand tile (128 for X, NT for W): fixes the leading byte offset between 16-byte K groups
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(const void* smem_ptr, int rows) {
   // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout_type=0 [61,64)
   const uint32_t addr = smem_u32(smem_ptr);
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((TCM * 16) >> 4) << 16;      // leading byte offset: next 16-byte K group
+  d |= (uint64_t)((rows * 16) >> 4) << 16;     // leading byte offset: next 16-byte K group
   d |= (uint64_t)(128 >> 4) << 32;             // stride byte offset: next 8-row group
   d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
   return d;
@@ -112,80 +113,101 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
   lo = __uint_as_float(l);
 }
+__device__ __forceinline__ float4 split_tf32_4(const float4 v, float4& lo) {
+  float4 hi;
+  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+  return hi;
+}
 
-__device__ int g_tc_dbg = 0;   // experiment switches (tools/tc_gemm_test.py, env GLAMR_TC_DEBUG); 0 in production
+__device__ int g_tc_dbg = 0;   // experiment switches (tools/tc_gemm_exp.py, env GLAMR_TC_DEBUG); 0 in production
 constexpr int kTcThreads = 256;
 constexpr int kTcStages = 2;
-constexpr size_t kTcSmemBytesTotal = (size_t)kTcStages * 4 * kTcTileFloats * sizeof(float) + 64;
+template <int NT>
+struct TcCfg {
+  static constexpr int kBTileFloats = NT * TCK;
+  static constexpr int kStageFloats = 2 * kTcATileFloats + 2 * kBTileFloats;            // Xhi | Xlo | Whi | Wlo
+  static constexpr int kXVec = (TCM * TCK / 4) / kTcThreads;                            // 16-byte loads per thread and K step
+  static constexpr int kWVec = (NT * TCK / 4) / kTcThreads;
+  static constexpr size_t kSmemBytes = (size_t)kTcStages * kStageFloats * sizeof(float) + 64;
+  static_assert(kWVec >= 1, "W tile smaller than one 16-byte load per thread");
+};
 
-// one K step (32 columns) of the 128-row X tile and the 128-row W tile, in flight in registers: 8 x 16 bytes per thread
+// one K step (32 columns) of the 128-row X tile and the NT-row W tile, in flight in registers
+template <int NT>
 struct TcRegs {
-  float4 x[(TCM * TCK / 4) / kTcThreads], w[(TCM * TCK / 4) / kTcThreads];
+  float4 x[TcCfg<NT>::kXVec], w[TcCfg<NT>::kWVec];
 };
 template <bool VEC>
-__device__ __forceinline__ void tc_load_tiles(TcRegs& r, int tid, int M, int N, int K, const float* __restrict__ X, int ldx,
+__device__ __forceinline__ float4 tc_load_row4(const float* __restrict__ P, int ld, int row, int nrows, int k, int K) {
+  if (VEC) {
+    if (row < nrows && k < K) return __ldg(reinterpret_cast<const float4*>(P + (size_t)row * ld + k));
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float a[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) a[q] = (row < nrows && k + q < K) ? P[(size_t)row * ld + k + q] : 0.0f;
+  return make_float4(a[0], a[1], a[2], a[3]);
+}
+template <int NT, bool VEC>
+__device__ __forceinline__ void tc_load_tiles(TcRegs<NT>& r, int tid, int M, int N, int K, const float* __restrict__ X, int ldx,
                                               const float* __restrict__ W, int m0, int n0, int k0) {
 #pragma unroll
-  for (int i = 0; i < (TCM * TCK / 4) / kTcThreads; ++i) {
+  for (int i = 0; i < TcCfg<NT>::kXVec; ++i) {
     const int idx = tid + i * kTcThreads;
-    const int row = idx & 127, kg = idx >> 7;        // row, 16-byte K group (0..7)
-    const int k = k0 + kg * 4;
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), wv = xv;
-    if (VEC) {
-      if (m0 + row < M && k < K) xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m0 + row) * ldx + k));
-      if (n0 + row < N && k < K) wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + row) * K + k));
-    } else {
-      float xa[4], wa[4];
+    r.x[i] = tc_load_row4<VEC>(X, ldx, m0 + (idx & (TCM - 1)), M, k0 + (idx / TCM) * 4, K);      // row, 16-byte K group (0..7)
+  }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        xa[q] = (m0 + row < M && k + q < K) ? X[(size_t)(m0 + row) * ldx + k + q] : 0.0f;
-        wa[q] = (n0 + row < N && k + q < K) ? W[(size_t)(n0 + row) * K + k + q] : 0.0f;
-      }
-      xv = make_float4(xa[0], xa[1], xa[2], xa[3]);
-      wv = make_float4(wa[0], wa[1], wa[2], wa[3]);
-    }
-    r.x[i] = xv;
-    r.w[i] = wv;
+  for (int i = 0; i < TcCfg<NT>::kWVec; ++i) {
+    const int idx = tid + i * kTcThreads;
+    r.w[i] = tc_load_row4<VEC>(W, K, n0 + (idx & (NT - 1)), N, k0 + (idx / NT) * 4, K);
   }
 }
 // split into tf32 hi / lo and store as K-major 8x16-byte core matrices (the layout umma_desc_kmajor_noswizzle describes)
-__device__ __forceinline__ void tc_store_tiles(float* st, int tid, const TcRegs& r) {
+template <int NT>
+__device__ __forceinline__ void tc_store_tiles(float* st, int tid, const TcRegs<NT>& r) {
   float* Ahi = st;
-  float* Alo = st + kTcTileFloats;
-  float* Bhi = st + 2 * kTcTileFloats;
-  float* Blo = st + 3 * kTcTileFloats;
+  float* Alo = st + kTcATileFloats;
+  float* Bhi = st + 2 * kTcATileFloats;
+  float* Blo = Bhi + TcCfg<NT>::kBTileFloats;
 #pragma unroll
-  for (int i = 0; i < (TCM * TCK / 4) / kTcThreads; ++i) {
+  for (int i = 0; i < TcCfg<NT>::kXVec; ++i) {
     const int idx = tid + i * kTcThreads;
-    const int row = idx & 127, kg = idx >> 7;
-    const float4 xv = r.x[i], wv = r.w[i];
-    float4 xh, xl, wh, wl;
-    split_tf32(xv.x, xh.x, xl.x); split_tf32(xv.y, xh.y, xl.y); split_tf32(xv.z, xh.z, xl.z); split_tf32(xv.w, xh.w, xl.w);
-    split_tf32(wv.x, wh.x, wl.x); split_tf32(wv.y, wh.y, wl.y); split_tf32(wv.z, wh.z, wl.z); split_tf32(wv.w, wh.w, wl.w);
-    const int off = (kg * TCM + row) * 4;
-    *reinterpret_cast<float4*>(Ahi + off) = xh;
-    *reinterpret_cast<float4*>(Alo + off) = xl;
-    *reinterpret_cast<float4*>(Bhi + off) = wh;
-    *reinterpret_cast<float4*>(Blo + off) = wl;
+    const int off = ((idx / TCM) * TCM + (idx & (TCM - 1))) * 4;
+    float4 lo;
+    const float4 hi = split_tf32_4(r.x[i], lo);
+    *reinterpret_cast<float4*>(Ahi + off) = hi;
+    *reinterpret_cast<float4*>(Alo + off) = lo;
+  }
+#pragma unroll
+  for (int i = 0; i < TcCfg<NT>::kWVec; ++i) {
+    const int idx = tid + i * kTcThreads;
+    const int off = ((idx / NT) * NT + (idx & (NT - 1))) * 4;
+    float4 lo;
+    const float4 hi = split_tf32_4(r.w[i], lo);
+    *reinterpret_cast<float4*>(Bhi + off) = hi;
+    *reinterpret_cast<float4*>(Blo + off) = lo;
   }
 }
 
 // 256 threads; two shared-memory stages: while the tensor core works on stage s (12 UTCHMMA per K step, tracked by
 // tcgen05.commit -> mbarrier[s]) all threads split and store K step it+1 into stage s^1 and already have the global
 // loads of step it+2 in flight in registers, so the L2 latency never sits on the critical path of these small GEMMs.
-template <int ACT, bool VEC>
+// NT = 128: 128x128 tiles (one CTA per SM).  NT = 32: 128x32 tiles for problems one tile high (M <= 128, a single
+// 120-frame window): 4x more CTAs, each with a quarter of the W traffic, split work and epilogue.
+template <int ACT, bool VEC, int NT>
 __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, int N, int K, const float* __restrict__ X, int ldx,
                                                                          const float* __restrict__ W, const float* __restrict__ bias,
                                                                          const float* __restrict__ bias2, float* __restrict__ Y, int ldy) {
+  using Cfg = TcCfg<NT>;
   extern __shared__ __align__(128) unsigned char tc_smem[];
   float* stage0 = reinterpret_cast<float*>(tc_smem);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + kTcStages * 4 * kTcTileFloats);   // [2]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + kTcStages * Cfg::kStageFloats);   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * TCM, n0 = blockIdx.x * TCN;
+  const int m0 = blockIdx.y * TCM, n0 = blockIdx.x * NT;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(NT));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 0) {
@@ -195,27 +217,28 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
   }
   const int nk = (K + TCK - 1) / TCK;
   const int dbg = g_tc_dbg;
-  TcRegs regs;
-  tc_load_tiles<VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, 0);
-  tc_store_tiles(stage0, tid, regs);
-  if (nk > 1) tc_load_tiles<VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, TCK);
+  TcRegs<NT> regs;
+  tc_load_tiles<NT, VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, 0);
+  tc_store_tiles<NT>(stage0, tid, regs);
+  if (nk > 1) tc_load_tiles<NT, VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, TCK);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
 
   for (int it = 0; it < nk; ++it) {
     const int s = it & 1;
-    float* st = stage0 + s * 4 * kTcTileFloats;
+    float* st = stage0 + s * Cfg::kStageFloats;
     if (tid == 0) {
 #pragma unroll
       for (int k8 = 0; k8 < ((dbg & 1) ? 0 : TCK / 8); ++k8) {           // one tf32 MMA consumes K = 8 (two 16-byte K groups)
-        const size_t koff = (size_t)k8 * 2 * TCM * 4;   // floats
-        const uint64_t dah = umma_desc_kmajor_noswizzle(st + koff), dal = umma_desc_kmajor_noswizzle(st + kTcTileFloats + koff);
-        const uint64_t dbh = umma_desc_kmajor_noswizzle(st + 2 * kTcTileFloats + koff), dbl = umma_desc_kmajor_noswizzle(st + 3 * kTcTileFloats + koff);
+        const size_t koa = (size_t)k8 * 2 * TCM * 4, kob = (size_t)k8 * 2 * NT * 4;   // floats
+        const uint64_t dah = umma_desc_kmajor_noswizzle(st + koa, TCM), dal = umma_desc_kmajor_noswizzle(st + kTcATileFloats + koa, TCM);
+        const uint64_t dbh = umma_desc_kmajor_noswizzle(st + 2 * kTcATileFloats + kob, NT);
+        const uint64_t dbl = umma_desc_kmajor_noswizzle(st + 2 * kTcATileFloats + Cfg::kBTileFloats + kob, NT);
         umma_tf32(tmem_d, dah, dbh, idesc, (it > 0 || k8 > 0) ? 1u : 0u);
         umma_tf32(tmem_d, dal, dbh, idesc, 1u);
         umma_tf32(tmem_d, dah, dbl, idesc, 1u);
@@ -226,8 +249,8 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
     if (it + 1 < nk) {
       // stage s^1 was consumed by the MMAs of step it-1: wait for their commit, then refill it while step `it` computes
       if (it >= 1) mbar_wait(&bar[s ^ 1], ((it - 1) >> 1) & 1);
-      if (!(dbg & 2)) tc_store_tiles(stage0 + (s ^ 1) * 4 * kTcTileFloats, tid, regs);
-      if (it + 2 < nk && !(dbg & 8)) tc_load_tiles<VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, (it + 2) * TCK);
+      if (!(dbg & 2)) tc_store_tiles<NT>(stage0 + (s ^ 1) * Cfg::kStageFloats, tid, regs);
+      if (it + 2 < nk && !(dbg & 8)) tc_load_tiles<NT, VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, (it + 2) * TCK);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
     }
@@ -235,12 +258,12 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
   mbar_wait(&bar[(nk - 1) & 1], ((nk - 1) >> 1) & 1);      // all MMAs done: the accumulator is final
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---- epilogue: a warp may read TMEM lanes (= rows) 32 (w % 4) .. +31; warps 0-3 take columns 0-63, warps 4-7 columns 64-127
+  // ---- epilogue: a warp may read TMEM lanes (= rows) 32 (w % 4) .. +31; 32-column chunks alternate between warps 0-3 and 4-7
   if (!(dbg & 4)) {
     const int wq = warp & 3, wh = warp >> 2;
     const int m = m0 + wq * 32 + lane;
 #pragma unroll 1
-    for (int cc = wh * (TCN / 64); cc < (wh + 1) * (TCN / 64); ++cc) {
+    for (int cc = wh; cc < NT / 32; cc += 2) {
       if (n0 + cc * 32 >= N) break;
       uint32_t v[32];
       const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(cc * 32);
@@ -279,7 +302,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
       } else if (m < M) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int n = n0 + cc * 32 + j;
+          const int n = nb + j;
           if (n < N) {
             float o = __uint_as_float(v[j]) + (bias ? bias[n] : 0.0f) + (bias2 ? bias2[n] : 0.0f);
             if (ACT == 1) o = fmaxf(o, 0.0f);
@@ -291,7 +314,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TCN));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(NT));
 }
 
 static int g_gemm_mode = 1;   // 1 = tcgen05 3xTF32 for the transformer (default), 0 = FP32 SIMT everywhere (A/B verification)
@@ -303,32 +326,45 @@ struct ScopedFp32Gemm {
   ~ScopedFp32Gemm() { g_gemm_mode = saved; }
 };
 
+template <int NT>
+static int gemm_tc_launch(cudaStream_t s, int M, int N, int K, const float* X, int ldx, const float* W, const float* b, const float* b2,
+                          float* Y, int ldy, int act) {
+  static bool attr = false;
+  constexpr size_t smem = TcCfg<NT>::kSmemBytes;
+  if (!attr) {
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid((N + NT - 1) / NT, (M + TCM - 1) / TCM);
+  const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)X | (uintptr_t)W) % 16 == 0);
+  if (vec) {
+    if (act == 1) gemm_tf32x3_tcgen05_kernel<1, true, NT><<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+    else gemm_tf32x3_tcgen05_kernel<0, true, NT><<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+  } else {
+    if (act == 1) gemm_tf32x3_tcgen05_kernel<1, false, NT><<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+    else gemm_tf32x3_tcgen05_kernel<0, false, NT><<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+  }
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+
 static int gemm(cudaStream_t s, int M, int N, int K, const float* X, int ldx, const float* W, const float* b, const float* b2, float* Y,
                 int ldy, int act) {
   if (g_gemm_mode == 1) {
-    static bool attr = false;
-    if (!attr) {
+    static int ntile = -1;     // GLAMR_TC_NTILE = 32 | 128 forces one tile shape (experiments); default: by problem height
+    if (ntile < 0) {
       if (const char* e = getenv("GLAMR_TC_DEBUG")) {
         const int v = atoi(e);
         GLAMR_CUDA_TRY(cudaMemcpyToSymbol(g_tc_dbg, &v, sizeof(int)));
       }
-      GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
-      GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
-      GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
-      GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytesTotal));
-      attr = true;
+      const char* t = getenv("GLAMR_TC_NTILE");
+      ntile = t ? atoi(t) : 0;
     }
-    dim3 grid((N + TCN - 1) / TCN, (M + TCM - 1) / TCM);
-    const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)X | (uintptr_t)W) % 16 == 0);
-    if (vec) {
-      if (act == 1) gemm_tf32x3_tcgen05_kernel<1, true><<<grid, kTcThreads, kTcSmemBytesTotal, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
-      else gemm_tf32x3_tcgen05_kernel<0, true><<<grid, kTcThreads, kTcSmemBytesTotal, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
-    } else {
-      if (act == 1) gemm_tf32x3_tcgen05_kernel<1, false><<<grid, kTcThreads, kTcSmemBytesTotal, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
-      else gemm_tf32x3_tcgen05_kernel<0, false><<<grid, kTcThreads, kTcSmemBytesTotal, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
-    }
-    GLAMR_LAUNCH_CHECK();
-    return GLAMR_OK;
+    const bool narrow = ntile == 32 || (ntile != 128 && M <= TCM);
+    return narrow ? gemm_tc_launch<32>(s, M, N, K, X, ldx, W, b, b2, Y, ldy, act) : gemm_tc_launch<128>(s, M, N, K, X, ldx, W, b, b2, Y, ldy, act);
   }
   dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
   if (act == 1)
