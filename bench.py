@@ -315,7 +315,9 @@ def run_ours(args):
             'clocks': clocks,
             'gpu_launches': 6 * K,
             'e2e': {'value': units * K / e2e_s, 'unit': 'frame*person*iter/s', 'h2d_bytes_per_step': h2d / K, 'd2h_bytes_per_step': d2h / K,
-                    'seconds': e2e_s, 'what': f'GlobalReconOptimizer.optimize(in_dict numpy)->numpy dict incl. init_data, {K} iterations'},
+                    'seconds': e2e_s, 'what': f'GlobalReconOptimizer.optimize(in_dict numpy)->numpy dict incl. init_data, {K} iterations',
+                    'phase_seconds': {k: round(v, 5) for k, v in e2e_model.phase_seconds.items()},
+                    'loop_ms_per_iter': round(e2e_model.iter_ms[-1][2], 5)},
             'roofline': {'bound': 'hbm', 'kernel': 'lbs_kernel', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                          'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes': alg_bytes, 'kernel_ms': lbs_ms, 'kernel_share_of_step': lbs_ms / (cold_ms / K),

@@ -409,7 +409,11 @@ extern "C" int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* pb,
   st->pb = *pb;
   st->gen++;
   compute_gs(st);
-  if (reset_adam) {
+  if (reset_adam & 2) {      // handle re-used for a new sequence: scratch (incl. tickets, moments) back to its initial zeros
+    GLAMR_CUDA_TRY(cudaMemsetAsync(st->arena, 0, st->arena_bytes, (cudaStream_t)stream));
+    reset_adam |= 1;
+  }
+  if (reset_adam & 1) {
     cudaStream_t s = (cudaStream_t)stream;
     GLAMR_CUDA_TRY(cudaMemsetAsync(st->adam.m, 0, sizeof(float) * pb->n_params, s));
     GLAMR_CUDA_TRY(cudaMemsetAsync(st->adam.v, 0, sizeof(float) * pb->n_params, s));

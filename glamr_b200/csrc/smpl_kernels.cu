@@ -89,16 +89,12 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(SmplDev m, int n, const 
     jp[0] = Gt[0]; jp[1] = Gt[1]; jp[2] = Gt[2];
     float GJ[3];
     mat3_vec(GR, J, GJ);
-    // A_j (3x4 row-major, 12 floats) stored tile-major and frame-minor: [n/32][j][c][n%32], so the LBS kernel fetches
-    // a CTA's [24][12][32] tile with one bulk copy and reads it with the frame on the lane axis (conflict free)
-    float* A = w.A + (((size_t)(f >> 5) * kNJ + j) * 12) * 32 + (f & 31);
+    // A_j (3x4 row-major, 12 floats) stored tile-major: [n/32][j][n%32][12], so the LBS kernel fetches a CTA's
+    // [24][32][12] tile with one bulk copy and a lane (= frame) reads its 12 floats with three LDS.128 (48-byte lane
+    // stride: the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups)
+    float4* A = reinterpret_cast<float4*>(w.A + (((size_t)(f >> 5) * kNJ + j) * 32 + (f & 31)) * 12);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      A[(i * 4 + 0) * 32] = GR[i * 3 + 0];
-      A[(i * 4 + 1) * 32] = GR[i * 3 + 1];
-      A[(i * 4 + 2) * 32] = GR[i * 3 + 2];
-      A[(i * 4 + 3) * 32] = Gt[i] - GJ[i];
-    }
+    for (int i = 0; i < 3; ++i) A[i] = make_float4(GR[i * 3 + 0], GR[i * 3 + 1], GR[i * 3 + 2], Gt[i] - GJ[i]);
   }
 }
 
@@ -113,7 +109,7 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(SmplDev m, int n, const 
 // version (3 x 16 tile) needed 19 wavefronts per 48 FFMA and stalled on the LSU (profiles/lbs_kernel_r01.md).
 // All operands arrive by 1-D bulk TMA (cp.async.bulk + mbarrier): the CTA's posedirs slab [207][384] in 23 chunks of
 // 9 rows (13,824 B contiguous thanks to the tile-major re-layout), the matching [9][32] pose-feature chunk, and the
-// A tile [32][24][12]; a 3-stage full/empty mbarrier ring replaces __syncthreads in the main loop.
+// A tile [24][32][12]; a 3-stage full/empty mbarrier ring replaces __syncthreads in the main loop.
 constexpr int kFramesPerCta = 32;
 constexpr int kFramesPerWarp = 8;
 constexpr int kVertsPerThread = 4;
@@ -135,7 +131,7 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* PDs = reinterpret_cast<float*>(smem_raw);              // [kStages][9][384]
   float* pfs = PDs + kStages * kChunkFloats;                     // [kStages][9][32]
-  float* As = PDs + kStageRegionFloats;                          // [24][12][32]  (frame-minor)
+  float* As = PDs + kStageRegionFloats;                          // [24][32 frames][12]
   float* bs = As + kATileFloats;                                 // [32][10]
   uint64_t* full = reinterpret_cast<uint64_t*>(bs + kFramesPerCta * kNB);   // [kStages]
   uint64_t* empty = full + kStages;                              // [kStages]
@@ -284,8 +280,8 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
   __syncthreads();
 
   // ---- skinning: warp w owns vertices 32w..32w+31 of the tile, lane = frame.  Joint indices / weights are
-  // warp-uniform (prefetched one vertex per lane, broadcast with shuffles), A is read frame-minor: every LDS is
-  // conflict free.
+  // warp-uniform (prefetched one vertex per lane, broadcast with shuffles), a lane reads its frame's A_j with three
+  // LDS.128: every LDS is conflict free.
   const int fr = lane;
   const int n = f0 + fr;
   const bool n_ok = n < n_end;
@@ -307,13 +303,19 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
         const int ci = __shfl_sync(0xffffffffu, my_ci, i);
         const int pos = ((((fr >> 2) ^ ((vi >> 2) & 7)) << 2) | (fr & 3));
         const float x = VP[(vi * 3 + 0) * 32 + pos], y = VP[(vi * 3 + 1) * 32 + pos], z = VP[(vi * 3 + 2) * 32 + pos];
-        const float* a0 = As + (jj & 0xff) * 12 * 32 + fr;
-        const float* a1 = As + ((jj >> 8) & 0xff) * 12 * 32 + fr;
-        const float* a2 = As + ((jj >> 16) & 0xff) * 12 * 32 + fr;
-        const float* a3 = As + ((jj >> 24) & 0xff) * 12 * 32 + fr;
+        const float4* a0 = reinterpret_cast<const float4*>(As + ((jj & 0xff) * 32 + fr) * 12);
+        const float4* a1 = reinterpret_cast<const float4*>(As + (((jj >> 8) & 0xff) * 32 + fr) * 12);
+        const float4* a2 = reinterpret_cast<const float4*>(As + (((jj >> 16) & 0xff) * 32 + fr) * 12);
+        const float4* a3 = reinterpret_cast<const float4*>(As + (((jj >> 24) & 0xff) * 32 + fr) * 12);
         float T[12];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) T[k] = fmaf(w3, a3[k * 32], fmaf(w2, a2[k * 32], fmaf(w1, a1[k * 32], w0 * a0[k * 32])));
+        for (int r = 0; r < 3; ++r) {
+          const float4 q0 = a0[r], q1 = a1[r], q2 = a2[r], q3 = a3[r];
+          T[4 * r + 0] = fmaf(w3, q3.x, fmaf(w2, q2.x, fmaf(w1, q1.x, w0 * q0.x)));
+          T[4 * r + 1] = fmaf(w3, q3.y, fmaf(w2, q2.y, fmaf(w1, q1.y, w0 * q0.y)));
+          T[4 * r + 2] = fmaf(w3, q3.z, fmaf(w2, q2.z, fmaf(w1, q1.z, w0 * q0.z)));
+          T[4 * r + 3] = fmaf(w3, q3.w, fmaf(w2, q2.w, fmaf(w1, q1.w, w0 * q0.w)));
+        }
         const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
         const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
         const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
@@ -341,9 +343,9 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
         for (int s = 0; s < m.K; ++s) {
           const int jj = m.skin_j[(size_t)gv * m.K + s];
           const float wt = m.skin_w[(size_t)gv * m.K + s];
-          const float* a = As + jj * 12 * 32 + fr;
+          const float* a = As + (jj * 32 + fr) * 12;
 #pragma unroll
-          for (int k = 0; k < 12; ++k) T[k] = fmaf(wt, a[k * 32], T[k]);
+          for (int k = 0; k < 12; ++k) T[k] = fmaf(wt, a[k], T[k]);
         }
         const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
         const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));

@@ -31,7 +31,7 @@ struct SmplDev {
 };
 
 struct SmplWorkspace {
-  float* A;         // [n/32][24][12][32] relative joint transforms (3x4 row-major per joint), tile-major, frame-minor
+  float* A;         // [n/32][24][32][12] relative joint transforms (3x4 row-major per joint), tile-major
   float* pf;        // [n/32][23][9][32] pose feature (R_j - I), j = 1..23, tile-major for bulk TMA (208 floats per frame reserved)
   float* jposed;    // [n][24][3]   posed LBS joints
   float* vcompact;  // [n][S][3]    skinned support vertices

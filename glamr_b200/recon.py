@@ -425,8 +425,9 @@ class GlobalReconOptimizer:
 
     # ------------------------------------------------------------------------------------------------ device state
     def _attach(self, data):
-        """Pack the optimisation variables into theta, build the constant tables and create the CUDA handle."""
-        self._release()
+        """Pack the optimisation variables into theta and build the constant tables.  The CUDA handle (scratch arena,
+        Adam moments, captured iteration graph) is kept across calls while (P, T, J, n_params) stay the same."""
+        self._fresh_attach = True
         self._data = data
         self._layout = PB.make_layout(data, self._flags)
         self._theta = torch.zeros(self._layout.n_params, device=self.device)
@@ -459,12 +460,18 @@ class GlobalReconOptimizer:
         pb = self._comp.compile(self._theta, opt_variables, loss_cfg, stage, p_begin=self._p_range[0], p_end=self._p_range[1],
                                 owner=(self.rank == 0), lbs_mode=0 if self.lbs_mode == 'full' else 1)
         self._pb = pb
+        dims = (pb.P, pb.T, pb.J, pb.n_params)
+        if self._opt is not None and dims != getattr(self, '_opt_dims', None):
+            self._release()
         with torch.cuda.device(self.device):
             if self._opt is None:
                 self._opt = ctypes.c_void_p()
                 L.check(self._lib.glamr_opt_create(ctypes.byref(self._opt), self.smpl.handle, ctypes.byref(pb)), 'glamr_opt_create')
-            else:
-                L.check(self._lib.glamr_opt_set_problem(self._opt, ctypes.byref(pb), int(reset_adam), L.stream_ptr()), 'glamr_opt_set_problem')
+                self._opt_dims = dims
+            else:                                   # bit 1: a new sequence re-uses the handle -> scratch back to its initial zeros
+                flags = int(bool(reset_adam)) | (2 if self._fresh_attach else 0)
+                L.check(self._lib.glamr_opt_set_problem(self._opt, ctypes.byref(pb), flags, L.stream_ptr()), 'glamr_opt_set_problem')
+        self._fresh_attach = False
 
     def _backward(self):
         L.check(self._lib.glamr_opt_backward(self._opt, L.ptr(self._theta), L.ptr(self._reduce), L.stream_ptr()), 'glamr_opt_backward')
@@ -602,11 +609,13 @@ class GlobalReconOptimizer:
 
     def optimize(self, in_dict, continue_opt=False):
         """:572-589"""
+        t0 = time.perf_counter()
         if continue_opt:
             data = tensor_to(in_dict, self.device)
             self._attach(data)
         else:
             data = self.init_data(in_dict)
+        t1 = time.perf_counter()
         for stage, stage_specs in self.opt_stage_specs.items():
             opt_meta = {'stage': stage, 'opt_latent_start_iter': stage_specs.get('opt_latent_start_iter', 0)}
             self.optimize_main(data, stage_specs['opt_variables'], stage_specs['opt_lr'], stage_specs['opt_niters'],
@@ -614,7 +623,10 @@ class GlobalReconOptimizer:
             if stage_specs.get('reinitialize_cam', False):
                 data['cam_pose'][:] = data['cam_pose'][[0]]
                 data['cam_pose_inv'] = G.inverse_transform(data['cam_pose'])
+        t2 = time.perf_counter()
         out = tensor_to_numpy(data)
+        # host wall-clock of the three phases of the last call (init_data includes the learned prior; stages include the waits)
+        self.phase_seconds = {'init_data': t1 - t0, 'stages': t2 - t1, 'to_numpy': time.perf_counter() - t2}
         return out
 
 

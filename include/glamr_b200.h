@@ -202,8 +202,9 @@ typedef struct glamr_opt glamr_opt_t;
  * pointers are device pointers that must stay alive while the handle uses them). */
 int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, const glamr_problem_t* problem);
 int glamr_opt_destroy(glamr_opt_t* st);
-/* Re-read a modified problem description (new stage: weights, active mask, camera mode).  reset_adam != 0 zeroes the
- * Adam moments and step count: the reference builds a fresh torch.optim.Adam per stage (global_recon_model.py:548,:642). */
+/* Re-read a modified problem description (new stage: weights, active mask, camera mode; same P, T, J, n_params).
+ * reset_adam bit 0 zeroes the Adam moments and step count: the reference builds a fresh torch.optim.Adam per stage
+ * (global_recon_model.py:548,:642); bit 1 also zeroes all scratch (handle re-used for a new sequence). */
 int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* problem, int reset_adam, void* stream);
 /* length (floats) of the caller-owned reduce buffer: [grad (n_params) | un-normalised term sums (GLAMR_NUM_TERMS)] */
 size_t glamr_opt_reduce_count(const glamr_opt_t* st);
