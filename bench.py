@@ -34,6 +34,8 @@ BYTES_CONST = 19_595_160          # SMPL constants, fp32 dense
 BYTES_PER_FP = 1_460              # per frame-person reads + gradient writes + Adam traffic
 FLOPS_PER_FP = 15.85e6            # dense full-LBS forward
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+# dram__bytes_read.sum + dram__bytes_write.sum of one lbs_kernel launch, keyed by frame-persons per launch (ncu capture, profiles/)
+NCU_LBS_DRAM_BYTES = {300: 18942208}
 
 
 def parse():
@@ -319,7 +321,8 @@ def run_ours(args):
                     'phase_seconds': {k: round(v, 5) for k, v in e2e_model.phase_seconds.items()},
                     'loop_ms_per_iter': round(e2e_model.iter_ms[-1][2], 5)},
             'roofline': {'bound': 'hbm', 'kernel': 'lbs_kernel', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                         'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
+                         'traffic': NCU_LBS_DRAM_BYTES.get(n_local), 'traffic_source': 'profiles/lbs_kernel_r01_final.md (ncu --set full, dram__bytes_read + write, per launch)' if n_local in NCU_LBS_DRAM_BYTES else None,
+                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes': alg_bytes, 'kernel_ms': lbs_ms, 'kernel_share_of_step': lbs_ms / (cold_ms / K),
                          'fp32': {'achieved_tflops': fp32_tf, 'peak_tflops_nominal': FP32_NOMINAL_TFLOPS, 'frac': fp32_tf / FP32_NOMINAL_TFLOPS,
                                   'note': 'the fused full-LBS iteration is FP32-FMA bound with L2-resident constants (SURVEY §8d); HBM fraction is small by construction'}},
