@@ -159,6 +159,62 @@ __global__ void __launch_bounds__(kFrameThreads) camera_scatter_kernel(OptCtx c)
   if (s < c.pb.T) camera_scatter_to_persons(c, s);
 }
 
+// ---- cross-GPU reduction over NVLink peer memory (one process per GPU, buffers exchanged as CUDA IPC handles) --------
+// Every rank owns one buffer: [64 x u32 header | 2 slots x W sources x slot_elems x u64].  Header words: 0 = epochs
+// published by this rank, 1 = epochs consumed, 2 = error.  Flag-in-data protocol (no fences, which cost tens of
+// microseconds at system scope): iteration e (1-based, never reset) -- the last CTA of traj_cam_backward_kernel packs every
+// element of [grad | term sums] with the epoch into one 8-byte word {value, e} and PUSHES it into slot e & 1, source row
+// `rank`, of every rank's buffer (plain 8-byte stores over NVLink: value and tag arrive together); apply_kernel polls its
+// OWN memory until the word of each source carries tag e and sums the W values in rank order -- the same bits on every
+// rank.  Two slots suffice: a rank can be at most one iteration ahead of the slowest reader (its next apply needs that
+// reader's next push), so epoch e only ever overwrites epoch e - 2, which every rank has finished reading.
+struct PeerCtx {
+  int rank, world;
+  size_t slot_elems;                       // 8-byte words per (slot, source)
+  unsigned long long* bufs[GLAMR_MAX_PEERS];
+};
+constexpr int kPeerHeaderWords = 64;      // u32 words = 32 u64
+
+__device__ __forceinline__ void st_peer_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ size_t peer_row(const PeerCtx& pc, uint32_t e, int src) {
+  return kPeerHeaderWords / 2 + ((size_t)(e & 1u) * GLAMR_MAX_PEERS + src) * pc.slot_elems;
+}
+// last CTA of the backward pass: reduce_buf is final (all other CTAs fenced before their ticket)
+__device__ void peer_publish(const PeerCtx& pc, const float* reduce_buf, int count) {
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(pc.bufs[pc.rank]);
+  const uint32_t e = hdr[0] + 1u;
+  const size_t row = peer_row(pc, e, pc.rank);
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const unsigned long long w = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(reduce_buf[i]);
+    for (int r = 0; r < pc.world; ++r) st_peer_u64(pc.bufs[r] + row + i, w);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) hdr[0] = e;
+}
+// value of element i published by rank `src` for epoch e (spins on local memory until it has landed)
+__device__ __forceinline__ float peer_take(const PeerCtx& pc, uint32_t e, int src, int i) {
+  const unsigned long long* p = pc.bufs[pc.rank] + peer_row(pc, e, src) + i;
+  unsigned long long w = ld_peer_u64(p);
+  if ((uint32_t)(w >> 32) != e) {
+    const long long t0 = clock64();
+    do {
+      if (clock64() - t0 > 40000000000LL) {          // ~20 s: a rank died or left the loop; fail loudly instead of hanging the GPU
+        reinterpret_cast<uint32_t*>(pc.bufs[pc.rank])[2] = 1u;
+        __trap();
+      }
+      w = ld_peer_u64(p);
+    } while ((uint32_t)(w >> 32) != e);
+  }
+  return __uint_as_float((uint32_t)w);
+}
+
 // loss partials -> un-normalised term sums (reduce_buf tail); fixed camera: sum the per-frame gradients over T
 __device__ void reduce_tail(const OptCtx& c, const double* partial, int n_slots, float* reduce_buf, double* sm /*[8*16]*/) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -189,7 +245,7 @@ __device__ void reduce_tail(const OptCtx& c, const double* partial, int n_slots,
 // blocks [0,P): reverse trajectory codec of one person; blocks [P, P+cam_blocks): camera backward of 256 frames (modes
 // 0-2; mode 3 runs camera_backward/scatter kernels first).  The last CTA to finish folds all partial sums.
 __global__ void __launch_bounds__(kScanThreads) traj_cam_backward_kernel(OptCtx c, int with_cam, double* partial_traj, const double* partial_all,
-                                                                         int n_slots, float* reduce_buf, unsigned int* ticket) {
+                                                                         int n_slots, float* reduce_buf, unsigned int* ticket, PeerCtx pc) {
   __shared__ float sm[kScanThreads / 32 + 1];
   __shared__ double smd[(kScanThreads / 32) * GLAMR_NUM_TERMS];
   pdl_launch_dependents();
@@ -216,7 +272,13 @@ __global__ void __launch_bounds__(kScanThreads) traj_cam_backward_kernel(OptCtx 
     for (int i = threadIdx.x; i < len; i += kScanThreads) traj_back_post(c, p, i, acc);
   }
   block_reduce_terms(acc, partial_traj + (size_t)blockIdx.x * GLAMR_NUM_TERMS, smd);
-  if (grid_last_block(ticket)) reduce_tail(c, partial_all, n_slots, reduce_buf, smd);
+  if (grid_last_block(ticket)) {
+    reduce_tail(c, partial_all, n_slots, reduce_buf, smd);
+    if (pc.world > 1) {
+      __syncthreads();
+      peer_publish(pc, reduce_buf, c.pb.n_params + GLAMR_NUM_TERMS);
+    }
+  }
 }
 
 struct AdamState {
@@ -225,12 +287,12 @@ struct AdamState {
   double* beta_pow;   // [0] beta1^t, [1] beta2^t, [2] step count (as a double)
 };
 
-__device__ void write_losses(const OptCtx& c, const float* reduce_buf, float* loss_terms) {
+__device__ void write_losses(const OptCtx& c, const float* term_sums /*[NUM_TERMS] un-normalised*/, float* loss_terms) {
   double total = 0.0;
   for (int k = 0; k < GLAMR_NUM_TERMS; ++k) {
     float val = 0.0f;
     if (c.pb.term_enabled[k]) {
-      val = reduce_buf[c.pb.n_params + k] / c.pb.term_norm[k];
+      val = term_sums[k] / c.pb.term_norm[k];
       if (!c.pb.term_monitor[k]) total += (double)val * (double)c.pb.term_weight[k];
     }
     loss_terms[k] = val;
@@ -239,21 +301,33 @@ __device__ void write_losses(const OptCtx& c, const float* reduce_buf, float* lo
 }
 
 __global__ void __launch_bounds__(32) losses_kernel(OptCtx c, const float* __restrict__ reduce_buf, float* __restrict__ loss_terms) {
-  if (threadIdx.x == 0) write_losses(c, reduce_buf, loss_terms);
+  if (threadIdx.x == 0) write_losses(c, reduce_buf + c.pb.n_params, loss_terms);
 }
 
-// loss terms (block 0) + torch.optim.Adam step; the last CTA to finish advances the step count / beta powers
+// loss terms (block 0) + torch.optim.Adam step; the last CTA to finish advances the step count / beta powers.
+// pc.world > 1: the gradient is the rank-ordered sum of every GPU's published slot (peer memory), not reduce_buf.
 __global__ void __launch_bounds__(256) apply_kernel(OptCtx c, float* __restrict__ theta, const float* __restrict__ reduce_buf, double lr,
-                                                    AdamState ad, float* loss_terms, int hist_stride, unsigned int* ticket) {
+                                                    AdamState ad, float* loss_terms, int hist_stride, unsigned int* ticket, PeerCtx pc) {
   pdl_launch_dependents();
   pdl_wait();
   const double b1 = ad.beta_pow[0] * 0.9, b2 = ad.beta_pow[1] * 0.999, step = ad.beta_pow[2];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_terms) write_losses(c, reduce_buf, loss_terms + (hist_stride > 0 ? (size_t)step * hist_stride : 0));
+  const uint32_t epoch = pc.world > 1 ? reinterpret_cast<const uint32_t*>(pc.bufs[pc.rank])[1] + 1u : 0u;
+  auto grad_at = [&](int i) -> float {
+    if (pc.world <= 1) return reduce_buf[i];
+    float g = 0.0f;
+    for (int r = 0; r < pc.world; ++r) g += peer_take(pc, epoch, r, i);
+    return g;
+  };
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_terms) {
+    float sums[GLAMR_NUM_TERMS];
+    for (int k = 0; k < GLAMR_NUM_TERMS; ++k) sums[k] = grad_at(c.pb.n_params + k);
+    write_losses(c, sums, loss_terms + (hist_stride > 0 ? (size_t)step * hist_stride : 0));
+  }
   const float bc2s = (float)sqrt(1.0 - b2);
   const float step_size = (float)(lr / (1.0 - b1));
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.pb.n_params; i += gridDim.x * blockDim.x) {
     if (!c.pb.active[i]) continue;
-    const float g = reduce_buf[i];
+    const float g = grad_at(i);
     float m = ad.m[i], v = ad.v[i];
     m = m + 0.1f * (g - m);
     v = v * 0.999f + 0.001f * g * g;
@@ -266,12 +340,12 @@ __global__ void __launch_bounds__(256) apply_kernel(OptCtx c, float* __restrict_
     ad.beta_pow[0] = b1;
     ad.beta_pow[1] = b2;
     ad.beta_pow[2] = step + 1.0;
+    if (pc.world > 1) reinterpret_cast<uint32_t*>(pc.bufs[pc.rank])[1] = epoch;
   }
 }
 
 }  // namespace glamr
 
-// =================================================================================================== C ABI
 using namespace glamr;
 
 struct glamr_opt {
@@ -295,6 +369,7 @@ struct glamr_opt {
   cudaGraphExec_t iter_exec;
   const void* cap_theta; const void* cap_reduce; const void* cap_hist;
   double cap_lr; int cap_stride; unsigned long long cap_gen, gen;   // gen advances with every glamr_opt_set_problem
+  PeerCtx peer;               // world <= 1: single GPU (or the caller reduces reduce_buf itself between backward and apply)
 };
 
 extern "C" size_t glamr_sizeof_person(void) { return sizeof(glamr_person_t); }
@@ -427,8 +502,10 @@ extern "C" size_t glamr_opt_reduce_count(const glamr_opt_t* st) { return st ? (s
 
 #define GLAMR_MARK() do { if (st->timing == 2 && st->n_ev < 24) GLAMR_CUDA_TRY(cudaEventRecord(st->ev[st->n_ev++], s)); } while (0)
 
-extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream) {
+static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream, bool use_peers) {
   if (!st || !theta || !reduce_buf) return GLAMR_EINVAL;
+  PeerCtx pc = st->peer;
+  if (!use_peers) pc.world = 0;
   cudaStream_t s = (cudaStream_t)stream;
   st->n_ev = 0;
   GLAMR_MARK();
@@ -471,9 +548,12 @@ extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* re
   }
   const int n_slots = st->slots_res + pb.P + st->cam_blocks + (from_persons ? st->slots_cam : 0);
   GLAMR_CUDA_TRY(launch_pdl(16, traj_cam_backward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1, part_traj,
-                            (const double*)st->partial, n_slots, reduce_buf, st->tickets));
+                            (const double*)st->partial, n_slots, reduce_buf, st->tickets, pc));
   GLAMR_MARK();
   return GLAMR_OK;
+}
+extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream) {
+  return backward_impl(st, theta, reduce_buf, stream, false);
 }
 
 extern "C" int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms, void* stream) {
@@ -484,15 +564,72 @@ extern "C" int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float*
   return GLAMR_OK;
 }
 
-extern "C" int glamr_opt_apply(glamr_opt_t* st, float* theta, const float* reduce_buf, double lr, float* loss_terms,
-                               int loss_hist_stride, void* stream) {
+static int apply_impl(glamr_opt_t* st, float* theta, const float* reduce_buf, double lr, float* loss_terms, int loss_hist_stride,
+                      void* stream, bool use_peers) {
   if (!st || !theta || !reduce_buf) return GLAMR_EINVAL;
+  PeerCtx pc = st->peer;
+  if (!use_peers) pc.world = 0;
   cudaStream_t s = (cudaStream_t)stream;
   OptCtx c = make_ctx(st, theta, nullptr);
   const int blocks = (st->pb.n_params + 255) / 256;
   GLAMR_CUDA_TRY(launch_pdl(32, apply_kernel, dim3(blocks < 296 ? blocks : 296), dim3(256), 0, s, c, theta, reduce_buf, lr, st->adam, loss_terms,
-                            loss_hist_stride, st->tickets + 1));
+                            loss_hist_stride, st->tickets + 1, pc));
   GLAMR_MARK();
+  return GLAMR_OK;
+}
+extern "C" int glamr_opt_apply(glamr_opt_t* st, float* theta, const float* reduce_buf, double lr, float* loss_terms,
+                               int loss_hist_stride, void* stream) {
+  return apply_impl(st, theta, reduce_buf, lr, loss_terms, loss_hist_stride, stream, false);
+}
+
+// ---- peer memory (CUDA IPC) ---------------------------------------------------------------------------------------------
+extern "C" int glamr_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) return GLAMR_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  GLAMR_CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return (int)e; }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return GLAMR_OK;
+}
+extern "C" int glamr_peer_open(const unsigned char* handle64, void** dev_ptr) {
+  if (!handle64 || !dev_ptr) return GLAMR_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  GLAMR_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GLAMR_OK;
+}
+extern "C" int glamr_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return GLAMR_EINVAL;
+  GLAMR_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return GLAMR_OK;
+}
+extern "C" int glamr_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return GLAMR_EINVAL;
+  GLAMR_CUDA_TRY(cudaFree(dev_ptr));
+  return GLAMR_OK;
+}
+extern "C" size_t glamr_opt_peer_bytes(const glamr_opt_t* st) {
+  if (!st) return 0;
+  const size_t slot = ((size_t)st->pb.n_params + GLAMR_NUM_TERMS + 63) & ~(size_t)63;
+  return kPeerHeaderWords * sizeof(uint32_t) + 2 * (size_t)GLAMR_MAX_PEERS * slot * sizeof(unsigned long long);
+}
+extern "C" int glamr_opt_set_peers(glamr_opt_t* st, int rank, int world, void* const* bufs) {
+  if (!st || world < 0 || world > GLAMR_MAX_PEERS || (world > 1 && (!bufs || rank < 0 || rank >= world))) return GLAMR_EINVAL;
+  st->gen++;                                   // a captured iteration holds the old peer table
+  memset(&st->peer, 0, sizeof(st->peer));
+  if (world <= 1) return GLAMR_OK;
+  st->peer.rank = rank;
+  st->peer.world = world;
+  st->peer.slot_elems = ((size_t)st->pb.n_params + GLAMR_NUM_TERMS + 63) & ~(size_t)63;
+  for (int r = 0; r < world; ++r) {
+    if (!bufs[r]) return GLAMR_EINVAL;
+    st->peer.bufs[r] = (unsigned long long*)bufs[r];
+  }
   return GLAMR_OK;
 }
 
@@ -501,9 +638,10 @@ extern "C" int glamr_opt_iterate(glamr_opt_t* st, float* theta, float* reduce_bu
   if (!st || !theta || !reduce_buf || n_iters < 0) return GLAMR_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   int rc, done = 0;
+  const bool peers = st->peer.world > 1;      // W > 1: backward publishes, apply sums the peers' slots (no call in between)
   auto eager = [&](cudaStream_t q) -> int {
-    if ((rc = glamr_opt_backward(st, theta, reduce_buf, q))) return rc;
-    return glamr_opt_apply(st, theta, reduce_buf, lr, loss_terms, loss_hist_stride, q);
+    if ((rc = backward_impl(st, theta, reduce_buf, q, peers))) return rc;
+    return apply_impl(st, theta, reduce_buf, lr, loss_terms, loss_hist_stride, q, peers);
   };
   if (!use_graph || st->timing) {
     for (; done < n_iters; ++done)

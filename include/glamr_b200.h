@@ -253,6 +253,26 @@ enum glamr_read {
   GLAMR_R_TRAJ_LOCAL = 10,     /* [P,T,11]  traj_local (rows of the exist range, others 0) */
   GLAMR_R_SMPL_A = 11          /* [P,T,24,12] relative joint transforms of the last SMPL evaluation */
 };
+/* ---- multi-GPU without a library collective: gradient reduction over NVLink peer memory --------------------------
+ * One process per GPU.  Every rank allocates one buffer (glamr_peer_alloc; size glamr_opt_peer_bytes), ships its
+ * 64-byte CUDA IPC handle to the other ranks (any host channel, e.g. torch.distributed.all_gather_object), opens theirs
+ * (glamr_peer_open) and registers the table with glamr_opt_set_peers.  From then on, inside glamr_opt_iterate, the
+ * backward pass pushes every element of [grad | term sums], tagged with the iteration number in the same 8-byte word,
+ * into every rank's buffer, and the Adam kernel polls its own memory until the W tagged values of an element have
+ * landed and sums them in rank order (identical bits on every rank): the all-reduce of global_recon's shared camera
+ * gradient is fused into the Adam kernel -- no NCCL call, no fences, no host involvement, the whole
+ * loop stays one replayed CUDA graph.  The stand-alone
+ * glamr_opt_backward / glamr_opt_apply never touch peer memory (the caller reduces reduce_buf between them).
+ * world <= 1 clears the table.  All ranks must call glamr_opt_iterate with the same iteration counts; a rank that
+ * waits ~20 s for a peer traps (CUDA error) instead of hanging. */
+#define GLAMR_MAX_PEERS 8
+int glamr_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* ipc_handle_64_bytes);
+int glamr_peer_open(const unsigned char* ipc_handle_64_bytes, void** dev_ptr);
+int glamr_peer_close(void* dev_ptr);      /* a pointer from glamr_peer_open */
+int glamr_peer_free(void* dev_ptr);       /* a pointer from glamr_peer_alloc */
+size_t glamr_opt_peer_bytes(const glamr_opt_t* st);
+int glamr_opt_set_peers(glamr_opt_t* st, int rank, int world, void* const* bufs /* [world], own buffer included */);
+
 /* device pointer + element count of an internal output buffer (valid until the handle is destroyed) */
 int glamr_opt_read(glamr_opt_t* st, int what, const float** ptr, size_t* count);
 
