@@ -32,6 +32,7 @@ GLOBALOPT_CASES = [
     ('static_multi_p3_t30', 'glamr_static_multi', 3, 30, False, 5),
     ('dynamic_multi_p2_t32', 'glamr_dynamic_multi', 2, 32, False, 4),
     ('3dpw_p2_t80_gaps', 'glamr_3dpw', 2, 80, True, 4),
+    ('h36m_p1_t48_gaps', 'glamr_h36m', 1, 48, True, 4),
 ]
 
 
@@ -248,6 +249,11 @@ def main(only=None):
         np.savez_compressed(os.path.join(HERE, 'nets.npz'), **nets_vectors())
         return
     assets = make_smpl_assets(0)
+    if only is not None:                       # one global-opt case by name (adding a fixture without touching the others)
+        case = [c for c in GLOBALOPT_CASES if c[0] == only][0]
+        np.savez_compressed(os.path.join(HERE, f'globalopt_{case[0]}.npz'), **globalopt_case(assets, *case))
+        print('wrote', case[0])
+        return
     np.savez_compressed(os.path.join(HERE, 'rotations.npz'), **rotation_vectors())
     np.savez_compressed(os.path.join(HERE, 'traj_codec.npz'), **traj_vectors())
     np.savez_compressed(os.path.join(HERE, 'smpl.npz'), **smpl_vectors(assets))

@@ -6,7 +6,7 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
-GLOBALOPT_CASES = ['dynamic_p1_t40', 'static_p1_t24', 'static_multi_p3_t30', 'dynamic_multi_p2_t32', '3dpw_p2_t80_gaps']
+GLOBALOPT_CASES = ['dynamic_p1_t40', 'static_p1_t24', 'static_multi_p3_t30', 'dynamic_multi_p2_t32', '3dpw_p2_t80_gaps', 'h36m_p1_t48_gaps']
 
 
 def load_golden(name):
