@@ -157,9 +157,14 @@ def test_globalopt_matches_reference_golden(name, smpl_assets):
             got = hist[:n, L.TERM_INDEX[k]]
             # iteration 0 is a pure forward on identical variables; later iterations follow Adam steps of
             # ~lr*sign(g), where zero-gradient directions random-walk on rounding noise in BOTH implementations
-            # (see tests/test_globalopt_host_emu.py), so small monitors such as the smoothness terms drift by ~1 %.
+            # (see tests/test_globalopt_host_emu.py), so small terms such as the smoothness monitors drift by a few per cent
+            # (6.8 % after 3 steps in glamr_h36m, whose data terms carry weights of 1e4) ...
             np.testing.assert_allclose(got[:1], ref[:1], rtol=2e-3, atol=1e-5, err_msg=f'{stage} {k} (iteration 0)')
-            np.testing.assert_allclose(got, ref, rtol=3e-2, atol=1e-4, err_msg=f'{stage} {k}')
+            np.testing.assert_allclose(got, ref, rtol=1e-1, atol=1e-4, err_msg=f'{stage} {k}')
+        # ... while the weighted objective, dominated by the data terms, must track the reference closely at every iteration
+        terms = [k for k in specs['loss_cfg'] if not specs['loss_cfg'][k].get('monitor_only', False)]
+        ref_total = sum(specs['loss_cfg'][k]['weight'] * gold[f'loss/{stage}/{k}'] for k in terms)
+        np.testing.assert_allclose(hist[:n, L.NUM_TERMS], ref_total, rtol=3e-2, err_msg=f'{stage} weighted total')
     for pid, pd in data['person_data'].items():
         # frames without observations sit on ill-conditioned 6d rotations (the random-init prior emits |a1| << 1) where the
         # Adam rounding-noise walk of traj_local_rot is amplified; compare the observed frames
