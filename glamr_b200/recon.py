@@ -37,14 +37,51 @@ def tensor_to(x, device):
     return x
 
 
+_GROUP_CPU_TENSORS = False      # tests flip this to run the grouped-copy path on CPU tensors
+
+
 def tensor_to_numpy(x):
-    if isinstance(x, torch.Tensor):
-        return x.detach().cpu().numpy()
-    if isinstance(x, dict):
-        return {k: tensor_to_numpy(v) for k, v in x.items()}
-    if isinstance(x, (list, tuple)):
-        return type(x)(tensor_to_numpy(v) for v in x)
-    return x
+    """lib/utils/torch_utils.py:118 -- nested containers of tensors -> numpy.  The output dict of `optimize` holds several
+    hundred small tensors per person; instead of one synchronous device->host copy each, the tensors of one dtype are
+    concatenated on the device, copied once and split into views on the host (same values, shapes and dtypes)."""
+    leaves = []
+
+    def walk(v):
+        if isinstance(v, torch.Tensor):
+            leaves.append(v.detach())
+            return ('leaf', len(leaves) - 1)
+        if isinstance(v, dict):
+            return ('dict', {k: walk(u) for k, u in v.items()})
+        if isinstance(v, (list, tuple)):
+            return (type(v), [walk(u) for u in v])
+        return ('raw', v)
+    tree = walk(x)
+    arrays = [None] * len(leaves)
+    groups = {}
+    for i, t in enumerate(leaves):
+        groups.setdefault((t.dtype, t.device), []).append(i)
+    for (dtype, device), idx in groups.items():
+        if len(idx) == 1 or (device.type == 'cpu' and not _GROUP_CPU_TENSORS):
+            for i in idx:
+                arrays[i] = leaves[i].cpu().numpy()
+            continue
+        flat = torch.cat([leaves[i].reshape(-1) for i in idx]).cpu().numpy()
+        off = 0
+        for i in idx:
+            n = leaves[i].numel()
+            arrays[i] = flat[off:off + n].reshape(tuple(leaves[i].shape))
+            off += n
+
+    def build(node):
+        kind, v = node
+        if kind == 'leaf':
+            return arrays[v]
+        if kind == 'dict':
+            return {k: build(u) for k, u in v.items()}
+        if kind == 'raw':
+            return v
+        return kind(build(u) for u in v)
+    return build(tree)
 
 
 def rotmats_to_rotvec(mats):
@@ -55,9 +92,19 @@ def rotmats_to_rotvec(mats):
     the usual largest-diagonal quaternion branch and the rotation-vector scaling (series below 1e-3 rad)."""
     R = np.asarray(mats, dtype=np.float64).reshape(-1, 3, 3)
     for _ in range(2):
-        c = np.stack([np.cross(R[:, 1], R[:, 2]), np.cross(R[:, 2], R[:, 0]), np.cross(R[:, 0], R[:, 1])], axis=1)   # cofactors
-        det = np.einsum('ni,ni->n', R[:, 0], c[:, 0])
-        R = 0.5 * (R + c / det[:, None, None])
+        a, b, c = R[:, 0], R[:, 1], R[:, 2]                      # rows; cofactor rows are their cross products (explicit:
+        cof = np.empty_like(R)                                   # np.cross is several times slower on [n,3] operands)
+        cof[:, 0, 0] = b[:, 1] * c[:, 2] - b[:, 2] * c[:, 1]
+        cof[:, 0, 1] = b[:, 2] * c[:, 0] - b[:, 0] * c[:, 2]
+        cof[:, 0, 2] = b[:, 0] * c[:, 1] - b[:, 1] * c[:, 0]
+        cof[:, 1, 0] = c[:, 1] * a[:, 2] - c[:, 2] * a[:, 1]
+        cof[:, 1, 1] = c[:, 2] * a[:, 0] - c[:, 0] * a[:, 2]
+        cof[:, 1, 2] = c[:, 0] * a[:, 1] - c[:, 1] * a[:, 0]
+        cof[:, 2, 0] = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+        cof[:, 2, 1] = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
+        cof[:, 2, 2] = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+        det = a[:, 0] * cof[:, 0, 0] + a[:, 1] * cof[:, 0, 1] + a[:, 2] * cof[:, 0, 2]
+        R = 0.5 * (R + cof / det[:, None, None])
     d = np.stack([R[:, 0, 0], R[:, 1, 1], R[:, 2, 2], R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]], axis=1)
     choice = d.argmax(axis=1)
     q = np.empty((R.shape[0], 4))

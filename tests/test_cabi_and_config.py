@@ -73,3 +73,32 @@ def test_rotmats_to_rotvec_matches_scipy():
     rv[50:100] = rv[50:100] / np.linalg.norm(rv[50:100], axis=1, keepdims=True) * (np.pi - 1e-4)   # near pi
     mats = Rotation.from_rotvec(rv).as_matrix().astype(np.float32)                        # float32-accurate, as HybrIK stores them
     np.testing.assert_allclose(rotmats_to_rotvec(mats), Rotation.from_matrix(mats).as_rotvec(), atol=1e-10)
+
+
+def test_tensor_to_numpy_batched_copy_keeps_values_shapes_dtypes(monkeypatch):
+    """output conversion of optimize() (lib/utils/torch_utils.py:118): grouped device->host copies, same nested structure"""
+    from glamr_b200 import recon
+    g = torch.Generator().manual_seed(0)
+    data = {'a': torch.randn(3, 4, generator=g), 'flag': True, 'name': 'seq', 'n': 7, 'none': None,
+            'person_data': {0: {'x': torch.randn(5, generator=g), 'mask': torch.tensor([True, False, True]), 'k': torch.arange(6).reshape(2, 3),
+                                'd': torch.randn(2, 2, generator=g).double(), 'empty': torch.zeros(0, 6), 'scalar': torch.tensor(2.5)}},
+            'rel': {(0, 1): torch.randn(2, 4, 4, generator=g)}, 'lst': [torch.ones(2), (torch.zeros(1), 3)]}
+    # force the grouped path for CPU tensors too (on the product path the tensors are CUDA tensors)
+    monkeypatch.setattr(recon, '_GROUP_CPU_TENSORS', True, raising=False)
+    out = recon.tensor_to_numpy(data)
+
+    def check(a, b):
+        if isinstance(a, torch.Tensor):
+            assert isinstance(b, np.ndarray) and b.shape == tuple(a.shape) and b.dtype == a.numpy().dtype
+            np.testing.assert_array_equal(b, a.numpy())
+        elif isinstance(a, dict):
+            assert list(a.keys()) == list(b.keys())
+            for k in a:
+                check(a[k], b[k])
+        elif isinstance(a, (list, tuple)):
+            assert type(a) is type(b) and len(a) == len(b)
+            for u, v in zip(a, b):
+                check(u, v)
+        else:
+            assert a is b or a == b
+    check(data, out)

@@ -19,7 +19,8 @@ for st in cfg.opt_stage_specs.values():
 smpl = SMPL(assets, device=dev)
 mt = MotionTrajJointModel(cfg, dev, None, smpl, make_prior_states())
 model = GlobalReconOptimizer(cfg, dev, None, smpl=smpl, mt_model=mt)
-in_dict = syn.make_in_dict(assets, 1, T, seed=0, gaps=False)
+P = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+in_dict = syn.make_in_dict(assets, P, T, seed=0, gaps=False)
 model.optimize(copy.deepcopy(in_dict))
 torch.cuda.synchronize()
 for rep in range(2):
@@ -32,4 +33,5 @@ pr.enable()
 model.optimize(copy.deepcopy(in_dict))
 torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
+pstats.Stats(pr).sort_stats('cumulative').print_stats(40)
+pstats.Stats(pr).sort_stats('tottime').print_stats(25)
