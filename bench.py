@@ -205,7 +205,10 @@ def run_ours(args):
         model._backward()
         L.check(lib.glamr_opt_apply(model._opt, L.ptr(model._theta), L.ptr(model._reduce), float(specs['opt_lr']), L.ptr(hist), L.NUM_TERMS + 1,
                                     L.stream_ptr()), 'apply')
-    native = world == 1 or getattr(model, '_peer_ok', False)   # nothing between backward and apply -> the library's own graph
+    # The timed loops replay ONE captured iteration per step.  With the opt-in peer-memory reduction the capture is the
+    # library's own (glamr_opt_iterate); otherwise torch captures backward [+ NCCL all-reduce] + apply, which measured
+    # ~12 us per step faster than calling glamr_opt_iterate(n=1) from Python once per step (0.153 vs 0.168 ms flushed).
+    native = getattr(model, '_peer_ok', False)
     graph = None
     if native:
         def step():
