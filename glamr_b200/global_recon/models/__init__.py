@@ -1,6 +1,15 @@
-"""Same registry as the reference's ``global_recon/models/__init__.py:4-6``: ``cfg.grecon_model_name`` selects the class."""
-from glamr_b200.recon import GlobalReconOptimizer
+"""Optimiser registry of the drop-in package.
 
-model_dict = {
-    'global_recon_model': GlobalReconOptimizer
-}
+GLAMR's entry points look the optimiser class up by ``cfg.grecon_model_name`` (run_demo.py:59, run_dataset.py:64 of the
+reference); the only name its configs use is ``global_recon_model``, which resolves to the CUDA-backed class here.
+"""
+
+
+def _build_registry():
+    from glamr_b200.recon import GlobalReconOptimizer as cuda_optimizer
+    registry = dict()
+    registry['global_recon_model'] = cuda_optimizer
+    return registry
+
+
+model_dict = _build_registry()
