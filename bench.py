@@ -113,6 +113,8 @@ def cpu_port_timing(assets, in_dict, cfg, iters, warm=3):
     from oracle.nets import MotionTrajJoint
     from oracle.smpl import OracleSMPL
     cfg = copy.deepcopy(cfg)
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would time a single-threaded reference)
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     stage, specs = next(iter(cfg.opt_stage_specs.items()))
     st_m, st_t = make_prior_states(1234)
     model = OracleGlobalRecon(cfg, assets, mt_model=LatentInjector(MotionTrajJoint(st_m, st_t, OracleSMPL(assets)), 0))
