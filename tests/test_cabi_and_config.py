@@ -102,3 +102,48 @@ def test_tensor_to_numpy_batched_copy_keeps_values_shapes_dtypes(monkeypatch):
         else:
             assert a is b or a == b
     check(data, out)
+
+
+def test_load_smpl_assets_official_pickle_layout(tmp_path):
+    """on-disk SMPL model as smplx reads it (lib/models/smpl.py:274-279 -> smplx.SMPL.__init__): sparse J_regressor,
+    posedirs [6890,3,207], 300 shape components, kintree_table with 2^32-1 as the root's parent, faces under 'f'"""
+    import pickle
+    import scipy.sparse as sp
+    from glamr_b200.smpl import load_smpl_assets
+    rng = np.random.default_rng(0)
+    V = 6890
+    jr = np.zeros((24, V), np.float64)
+    for j in range(24):
+        idx = rng.choice(V, 8, replace=False)
+        jr[j, idx] = rng.dirichlet(np.ones(8))
+    parents = np.array([4294967295, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21], dtype=np.uint32)
+    model = {'v_template': rng.normal(size=(V, 3)), 'shapedirs': rng.normal(size=(V, 3, 300)).astype(np.float32),
+             'posedirs': rng.normal(size=(V, 3, 207)).astype(np.float32), 'J_regressor': sp.csc_matrix(jr),
+             'weights': rng.random((V, 24)), 'kintree_table': np.stack([parents, np.arange(24, dtype=np.uint32)]),
+             'f': rng.integers(0, V, size=(13776, 3)).astype(np.uint32)}
+    d = tmp_path / 'smpl'
+    d.mkdir()
+    with open(d / 'SMPL_NEUTRAL.pkl', 'wb') as fh:
+        pickle.dump(model, fh)
+    np.save(tmp_path / 'J_regressor_extra.npy', rng.random((9, V)))
+    a = load_smpl_assets(str(d), str(tmp_path / 'J_regressor_extra.npy'))
+    assert a['shapedirs'].shape == (V, 3, 10) and a['posedirs'].shape == (207, V * 3) and a['J_regressor'].shape == (24, V)
+    assert a['lbs_weights'].shape == (V, 24) and a['faces'].shape == (13776, 3) and a['J_regressor_extra'].shape == (9, V)
+    assert list(a['parents'][:4]) == [-1, 0, 0, 0]
+    # smplx: posedirs.reshape(-1, 207).T -> row k holds the offsets of every (vertex, coordinate) for pose feature k
+    np.testing.assert_array_equal(a['posedirs'][5].reshape(V, 3), model['posedirs'][:, :, 5])
+    np.testing.assert_allclose(a['J_regressor'], jr)
+
+
+def test_checkpoint_discovery_follows_reference_layout(tmp_path):
+    """lib/utils/tools.py:41-45,94-104: results/<cfg>/version_<latest>/checkpoints/*best*.ckpt"""
+    from glamr_b200.motion_traj import _find_checkpoint
+    root = tmp_path / 'results' / 'motion_filler' / 'motion_infiller_demo'
+    for v, names in {0: ['model-best-epoch=0003.ckpt'], 2: ['last.ckpt'], 10: ['model-best-epoch=0040.ckpt', 'last.ckpt']}.items():
+        d = root / f'version_{v}' / 'checkpoints'
+        d.mkdir(parents=True)
+        for n in names:
+            (d / n).write_bytes(b'')
+    assert _find_checkpoint(str(root)).endswith(os.path.join('version_10', 'checkpoints', 'model-best-epoch=0040.ckpt'))   # numeric, not lexical, order
+    with pytest.raises(FileNotFoundError):
+        _find_checkpoint(str(tmp_path / 'results' / 'traj_pred' / 'traj_pred_demo'))
