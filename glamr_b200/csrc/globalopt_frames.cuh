@@ -580,6 +580,29 @@ GLAMR_HD void camera_backward(const OptCtx& c, int t, TermAcc& acc) {
       }
       acc.v[GLAMR_T_CAM_ORIGIN_SMOOTH] += (double)(kFps2 * ss);
     }
+    if (pb.term_enabled[GLAMR_T_CAM_DEPTH_SMOOTH] && T > 1) {
+      // loss_func.py:94-103: velocity of the camera origin along the NEXT frame's optical axis (third column of
+      // cam_pose_inv[t+1]), squared and SUMMED over the T-1 frame pairs (the trailing .mean() acts on a 0-d tensor)
+      const float gs = c.gs[GLAMR_T_CAM_DEPTH_SMOOTH];
+      if (t + 1 < T) {            // pair (t, t+1): this frame is the "previous" origin
+        float d = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) d += (inv[a * 4 + 3] - inv[12 + a * 4 + 3]) * inv[12 + a * 4 + 2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) gti[a] += 2.0f * kFps2 * gs * d * inv[12 + a * 4 + 2];
+        acc.v[GLAMR_T_CAM_DEPTH_SMOOTH] += (double)(kFps2 * d * d);
+      }
+      if (t > 0) {                // pair (t-1, t): this frame supplies the origin that is subtracted and the axis
+        float d = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) d += (inv[-12 + a * 4 + 3] - inv[a * 4 + 3]) * inv[a * 4 + 2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          gti[a] -= 2.0f * kFps2 * gs * d * inv[a * 4 + 2];
+          gRi[a * 3 + 2] += 2.0f * kFps2 * gs * d * (inv[-12 + a * 4 + 3] - inv[a * 4 + 3]);
+        }
+      }
+    }
     if (pb.term_enabled[GLAMR_T_CAM_UP_REG]) {
       float w = (t < 10) ? pb.cam_up_first_weight : 1.0f;
       if (pb.cam_up_first_only && t > 0) w = 0.0f;

@@ -14,14 +14,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, 'libglamr_b200.so')
 CSRC = os.path.join(HERE, 'csrc')
 SOURCES = ['smpl_kernels.cu', 'globalopt_kernels.cu', 'c_api.cu', 'nets_kernels.cu']
-NUM_TERMS = 20
+NUM_TERMS = 21
 
 TERM_INDEX = {
     'kp_2d': 0, 'kp_2d_dist': 1, 'cam_traj_rot': 2, 'cam_traj_trans': 3, 'traj_rot_smoothness': 4,
     'traj_trans_smoothness': 5, 'rel_transform': 6, 'local_traj_dxy_reg': 7, 'local_traj_dheading_reg': 8,
     'local_traj_dheading_reg_new': 9, 'local_traj_rot_reg': 10, 'local_traj_z_reg': 11, 'traj_rot_res': 12,
     'traj_trans_res': 13, 'cam_inv_trans_residual_reg': 14, 'cam_inv_rot_smoothness': 15, 'cam_origin_smoothness': 16,
-    'cam_up_reg': 17, 'cam_rot_smoothness': 18, 'cam_trans_smoothness': 19,
+    'cam_up_reg': 17, 'cam_rot_smoothness': 18, 'cam_trans_smoothness': 19, 'cam_depth_smoothness': 20,
 }
 CAM_CONST, CAM_PER_FRAME, CAM_FIXED, CAM_FROM_PERSONS = 0, 1, 2, 3
 (R_ORIENT_WORLD, R_TRANS_WORLD, R_ORIENT_BASE, R_TRANS_BASE, R_KP_PRED, R_ORIENT_CIW, R_TRANS_CIW, R_CAM_POSE,

@@ -262,6 +262,7 @@ class StageCompiler:
             'local_traj_dheading_reg_new': sum(n - 1 for n in lens), 'local_traj_rot_reg': sum(lens), 'local_traj_z_reg': sum(lens),
             'traj_rot_res': P * T, 'traj_trans_res': P * T, 'cam_inv_trans_residual_reg': lay.trans_res_rows,
             'cam_inv_rot_smoothness': T - 1, 'cam_origin_smoothness': T - 1, 'cam_rot_smoothness': T - 1, 'cam_trans_smoothness': T - 1,
+            'cam_depth_smoothness': 1,          # loss_func.py:102 sums over the T-1 frame pairs (the .mean() sees a 0-d tensor)
         })
         if 'traj_rot_smoothness' in loss_cfg and loss_cfg['traj_rot_smoothness'].get('rot_type', '6d') != '6d':
             raise NotImplementedError("traj_rot_smoothness: only rot_type '6d' is implemented in the CUDA path")

@@ -128,7 +128,7 @@ enum glamr_term {
   GLAMR_T_TRAJ_TRANS_SMOOTH, GLAMR_T_REL_TRANSFORM, GLAMR_T_DXY_REG, GLAMR_T_DHEADING_REG, GLAMR_T_DHEADING_REG_NEW,
   GLAMR_T_ROT_REG, GLAMR_T_Z_REG, GLAMR_T_ROT_RES, GLAMR_T_TRANS_RES, GLAMR_T_CAM_INV_TRANS_RES_REG,
   GLAMR_T_CAM_INV_ROT_SMOOTH, GLAMR_T_CAM_ORIGIN_SMOOTH, GLAMR_T_CAM_UP_REG, GLAMR_T_CAM_ROT_SMOOTH,
-  GLAMR_T_CAM_TRANS_SMOOTH, GLAMR_NUM_TERMS
+  GLAMR_T_CAM_TRANS_SMOOTH, GLAMR_T_CAM_DEPTH_SMOOTH, GLAMR_NUM_TERMS
 };
 
 enum glamr_cam_mode {

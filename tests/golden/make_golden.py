@@ -244,7 +244,27 @@ def globalopt_case(assets, name, cfg_id, P, T, gaps, niters):
     return rec
 
 
+def camera_term_vectors():
+    """camera-only residuals that no shipped config enables (so the global-opt fixtures never exercise them), evaluated
+    by the reference's own functions on a seeded camera track"""
+    from global_recon.models import loss_func as ref_loss
+    from lib.utils.torch_transform import make_transform
+    g = torch.Generator().manual_seed(5)
+    T = 37
+    rot6d = torch.tensor([1., 0., 0., 0., 1., 0.]) + 0.2 * torch.randn(T, 6, generator=g)
+    trans = torch.cumsum(0.05 * torch.randn(T, 3, generator=g), dim=0)
+    inv = make_transform(rot6d, trans, rot_type='6d')
+    data = {'cam_pose_inv': inv}
+    rec = {'cam_rot6d': rot6d.numpy(), 'cam_trans': trans.numpy(), 'cam_pose_inv': inv.numpy()}
+    for name in ['cam_depth_smoothness', 'cam_origin_smoothness', 'cam_inv_rot_smoothness']:
+        rec[name] = np.asarray(float(ref_loss.loss_func_dict[name](data, {})))
+    return rec
+
+
 def main(only=None):
+    if only == 'camera_terms':
+        np.savez_compressed(os.path.join(HERE, 'camera_terms.npz'), **camera_term_vectors())
+        return
     if only == 'nets':
         np.savez_compressed(os.path.join(HERE, 'nets.npz'), **nets_vectors())
         return

@@ -52,7 +52,23 @@ def _param_views(runner, data, model, opt_variables):
 
 @pytest.mark.parametrize('name', GLOBALOPT_CASES)
 def test_gradients_and_steps_match_oracle(name, smpl_assets):
+    _check_case(name, smpl_assets)
+
+
+@pytest.mark.parametrize('name', ['dynamic_p1_t40', 'static_p1_t24', '3dpw_p2_t80_gaps'])
+def test_cam_depth_smoothness_term(name, smpl_assets):
+    """loss_func.py:94-103 is registered but used by no shipped config: switch it on in every stage (per-frame camera
+    variables, fixed camera, camera derived from the persons) and check value + gradient + steps like the other terms."""
+    def add_term(cfg):
+        for st in cfg.opt_stage_specs.values():
+            st['loss_cfg']['cam_depth_smoothness'] = {'weight': 3.0}
+    _check_case(name, smpl_assets, mutate=add_term)
+
+
+def _check_case(name, smpl_assets, mutate=None):
     gold, cfg, in_dict = case_setup(name, smpl_assets)
+    if mutate is not None:
+        mutate(cfg)
     ora = OracleGlobalRecon(cfg, smpl_assets, mt_model=ReplayMT(gold))
     data_o = ora.init_data(copy.deepcopy(in_dict))
     ora2 = OracleGlobalRecon(cfg, smpl_assets, mt_model=ReplayMT(gold))

@@ -115,3 +115,14 @@ def test_globalopt_trajectory_matches_reference(name, smpl_assets):
             if f'final/{pid}/{k}' in gold:
                 np.testing.assert_allclose(pd[k].detach().numpy(), gold[f'final/{pid}/{k}'], atol=1e-4, err_msg=f'final {pid} {k}')
     np.testing.assert_allclose(data['cam_pose'].numpy(), gold['final/cam_pose'], atol=1e-4)
+
+
+def test_camera_only_terms_match_reference_functions():
+    """residuals no shipped config enables (loss_func.py:76-103): the reference's own functions on a seeded camera track"""
+    import torch
+    from oracle.residuals import RESIDUALS
+    gold = load_golden('camera_terms')
+    data = {'cam_pose_inv': torch.tensor(gold['cam_pose_inv'])}
+    for name in ['cam_depth_smoothness', 'cam_origin_smoothness', 'cam_inv_rot_smoothness']:
+        got = float(RESIDUALS[name](data, {}))
+        assert abs(got - float(gold[name])) <= 1e-5 * abs(float(gold[name])), name
