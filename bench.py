@@ -292,7 +292,7 @@ def run_ours(args):
     L.check(lib.glamr_opt_kernel_timing(model._opt, 0), 'timing')
     lbs_ms = float(np.mean(lbs))
     _dbg('lbs timing done')
-    n_local = (model._p_range[1] - model._p_range[0]) * args.frames
+    n_local = model._n_range[1] - model._n_range[0]
 
     # ---------------- end to end through the public API with host buffers: optimize(in_dict numpy) -> numpy dict
     e2e_model = new_model()

@@ -547,7 +547,7 @@ GLAMR_HD void camera_backward(const OptCtx& c, int t, TermAcc& acc) {
   const glamr_problem_t& pb = c.pb;
   const int T = pb.T;
   float G[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // dL/dRc (9) , dL/dtc (3)
-  for (int p = pb.p_begin; p < pb.p_end; ++p) {
+  for (int p = 0; p < pb.P; ++p) {          // frame-persons of other ranks hold zeros (frame_residuals_kernel)
     const float* g = c.sc.g_cam + ((size_t)p * T + t) * 12;
 #pragma unroll
     for (int k = 0; k < 12; ++k) G[k] += g[k];

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c
   acc.clear();
   if (n < N) {
     const int p = n / c.pb.T, t = n - p * c.pb.T;
-    if (p >= c.pb.p_begin && p < c.pb.p_end) {
+    if (n >= c.pb.n_begin && n < c.pb.n_end) {
       const int nl = n - n_begin;
       const float* tw = c.sc.trans_world + (size_t)n * 3;
       const float sc = c.pb.scale_all ? c.pb.scale_all[n] : 1.0f;
@@ -520,7 +520,7 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   }
   GLAMR_MARK();
   // SMPL for the persons this rank owns (global_recon_model.py:517-524); tile-major scratch (A, pf) is local to the launch
-  const int n_begin = pb.p_begin * pb.T, n_end = pb.p_end * pb.T;
+  const int n_begin = pb.n_begin, n_end = pb.n_end;
   SmplWorkspace wo = st->ws;
   wo.jposed += (size_t)n_begin * kNJ * 3;
   wo.vcompact += (size_t)n_begin * st->smpl.S * 3;

@@ -49,7 +49,7 @@ class Person(ctypes.Structure):
 class Problem(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ['P', 'T', 'J', 'cam_mode', 'off_cam_rot', 'off_cam_trans', 'use_world_res', 'has_world_dheading',
-                 'trans_res_all', 'cam_up_first_only', 'n_params', 'p_begin', 'p_end', 'owner', 'lbs_mode', 'pad_']] + \
+                 'trans_res_all', 'cam_up_first_only', 'n_params', 'n_begin', 'n_end', 'owner', 'lbs_mode', 'pad_']] + \
                [('cam_up_first_weight', ctypes.c_float), ('rel_trans_weight', ctypes.c_float),
                 ('term_weight', ctypes.c_float * NUM_TERMS), ('term_norm', ctypes.c_float * NUM_TERMS),
                 ('term_enabled', ctypes.c_int32 * NUM_TERMS), ('term_monitor', ctypes.c_int32 * NUM_TERMS)] + \

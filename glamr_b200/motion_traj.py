@@ -172,15 +172,78 @@ class TrajPredVAE:
         return out
 
 
-def _find_checkpoint(cfg_dir, cp='best'):
-    """results/<cfg>/version_N/checkpoints/*best*.ckpt (lib/utils/tools.py:41-45,94-104)"""
-    versions = sorted(glob.glob(os.path.join(cfg_dir, 'version_*')), key=lambda p: int(p.rsplit('_', 1)[1]))
-    if not versions:
-        raise FileNotFoundError(f'no checkpoint versions under {cfg_dir}')
-    files = glob.glob(os.path.join(versions[-1], 'checkpoints', f'*{cp}*.ckpt'))
-    if not files:
-        raise FileNotFoundError(f'no *{cp}*.ckpt under {versions[-1]}/checkpoints')
-    return files[0]
+def load_lightning_state_dict(path):
+    """state_dict of a PyTorch-Lightning ``.ckpt`` (lib/utils/tools.py:94-104 -> ``load_from_checkpoint``) as plain float32
+    numpy arrays.  Lightning checkpoints pickle hyper-parameter objects next to the tensors; tensors-only loading
+    (``weights_only=True``) is tried first so that nothing but tensors is unpickled, the permissive path is the fall-back
+    for files that need it."""
+    try:
+        ck = torch.load(path, map_location='cpu', weights_only=True)
+    except Exception:
+        ck = torch.load(path, map_location='cpu', weights_only=False)
+    sd = ck.get('state_dict', ck)
+    return {k: (v.detach().float().numpy() if isinstance(v, torch.Tensor) else v) for k, v in sd.items()}
+
+
+def _find_checkpoint(cfg_dir, cp='best', version=None):
+    """lib/utils/tools.py:41-45 (find_last_version) + :94-104 (get_checkpoint_path): 'best' = the LAST of the sorted
+    *best*.ckpt names, 'last' = last.ckpt, an integer = model-epoch=NNNN.ckpt"""
+    if version is None:
+        numbers = sorted(int(os.path.basename(p)[len('version_'):]) for p in glob.glob(os.path.join(cfg_dir, 'version_*')))
+        if not numbers:
+            raise FileNotFoundError(f'no checkpoint versions under {cfg_dir}')
+        version = numbers[-1]
+    ck_dir = os.path.join(cfg_dir, f'version_{version}', 'checkpoints')
+    if cp == 'last':
+        return os.path.join(ck_dir, 'last.ckpt')
+    if cp == 'best':
+        files = sorted(glob.glob(os.path.join(ck_dir, '*best*.ckpt')))
+        if not files:
+            raise FileNotFoundError(f'no *best*.ckpt under {ck_dir}')
+        return files[-1]
+    return os.path.join(ck_dir, f'model-epoch={int(cp):04d}.ckpt')
+
+
+# motion_infiller/cfg_infer/joint_motion_traj_demo.yml (the only joint config the reference ships)
+_JOINT_DEMO_YML = {
+    'results_root_dir': 'results/motion_filler_infer', 'seed': 1,
+    'model_specs': {'mfiller_cfg': 'motion_infiller_demo', 'mfiller_cp': 'best', 'trajpred_cfg': 'traj_pred_demo', 'trajpred_cp': 'best'},
+    'amass_dir': 'datasets/amass_processed/v1', 'seq_len': 300, 'seq_sampling_method': 'length',
+    'data_mask_methods': {'drop_frames': {'preserve_first_n': 10, 'min_drop_len': 5, 'max_drop_len': 200}},
+    'num_motion_samp': 3, 'multi_step_mfiller': True, 'multi_step_trajpred': False,
+}
+_RESULTS_ROOT = {'motion_infiller': 'results/motion_filler', 'traj_pred': 'results/traj_pred'}   # results_root_dir of the two shipped network configs
+
+
+class MTConfig:
+    """motion_infiller/utils/config_motion_traj.py:7-45: the joint model's YAML (cwd-relative glob like the reference; the
+    shipped joint_motion_traj_demo.yml is built in) and the checkpoint directories of the two networks it names
+    (motion_infiller/utils/config.py:16-26, traj_pred/utils/config.py:16-26)."""
+
+    def __init__(self, cfg_id):
+        import yaml
+        self.id = cfg_id
+        files = glob.glob(f'motion_infiller/cfg_infer/**/{cfg_id}.yml', recursive=True)
+        if len(files) == 1:
+            self.yml_dict = yaml.safe_load(open(files[0]))
+        elif cfg_id == 'joint_motion_traj_demo':
+            self.yml_dict = {k: (dict(v) if isinstance(v, dict) else v) for k, v in _JOINT_DEMO_YML.items()}
+        else:
+            raise FileNotFoundError(f'motion_infiller/cfg_infer/**/{cfg_id}.yml not found')
+        y = self.yml_dict
+        self.model_specs = y.get('model_specs', {})
+        self.seed = y.get('seed', 1)
+        self.multi_step_mfiller = y.get('multi_step_mfiller', True)
+        self.multi_step_trajpred = y.get('multi_step_trajpred', True)
+
+    @staticmethod
+    def network_cfg_dir(package, net_cfg_id):
+        import yaml
+        files = glob.glob(f'{package}/cfg/**/{net_cfg_id}.yml', recursive=True)
+        root = _RESULTS_ROOT[package]
+        if len(files) == 1:
+            root = os.path.expanduser(yaml.safe_load(open(files[0])).get('results_root_dir', root))
+        return f'{root}/{net_cfg_id}'
 
 
 class MotionTrajJointModel:
@@ -189,17 +252,27 @@ class MotionTrajJointModel:
     def __init__(self, cfg=None, device=torch.device('cuda'), log=None, smpl=None, states=None):
         """cfg: config id / object of the joint model (only its checkpoint locations are used).  states: optional
         (infiller_state_dict, trajpred_state_dict); otherwise the reference's checkpoint files are loaded."""
-        self.cfg, self.device, self.log = cfg, L.require_cuda(device), log
-        self.multi_step_mfiller, self.multi_step_trajpred = True, False
+        self.device, self.log = L.require_cuda(device), log
+        if isinstance(cfg, str):
+            cfg = MTConfig(cfg)
+        self.cfg = cfg
+        self.multi_step_mfiller = getattr(cfg, 'multi_step_mfiller', True)
+        self.multi_step_trajpred = getattr(cfg, 'multi_step_trajpred', False)
+        if self.multi_step_trajpred:
+            raise NotImplementedError('multi_step_trajpred: chunked trajectory prediction is not implemented on CUDA (the shipped joint config disables it)')
         if smpl is None:
             from .smpl import SMPL
             smpl = SMPL(device=self.device)
         self.smpl = smpl
         if states is None:
+            specs = getattr(cfg, 'model_specs', None) or _JOINT_DEMO_YML['model_specs']
             states = []
-            for sub in ['results/motion_filler/motion_infiller_demo', 'results/traj_pred/traj_pred_demo']:
-                ck = torch.load(_find_checkpoint(sub), map_location='cpu', weights_only=False)
-                states.append(ck.get('state_dict', ck))
+            for package, key in [('motion_infiller', 'mfiller'), ('traj_pred', 'trajpred')]:
+                path = _find_checkpoint(MTConfig.network_cfg_dir(package, specs[f'{key}_cfg']), specs.get(f'{key}_cp', 'best'),
+                                        specs.get(f'{key}_version'))
+                if log is not None:
+                    log.info(f'loading {package} from check point {path}')
+                states.append(load_lightning_state_dict(path))
         self.mfiller = MotionInfillerVAE(states[0], self.device)
         self.traj_predictor = TrajPredVAE(states[1], self.device, self.smpl)
 

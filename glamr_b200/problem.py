@@ -171,15 +171,15 @@ class StageCompiler:
             norms['cam_traj_trans'] = nvis
         return kp_w, kp_dm, ctr_w, ctt_w, norms
 
-    def compile(self, theta, opt_variables, loss_cfg, stage, p_begin=0, p_end=None, owner=True, lbs_mode=0):
+    def compile(self, theta, opt_variables, loss_cfg, stage, n_begin=0, n_end=None, owner=True, lbs_mode=0):
         data, lay, fl, dev, P, T, J = self.data, self.layout, self.flags, self.device, self.P, self.T, self.J
-        p_end = P if p_end is None else p_end
+        n_end = P * T if n_end is None else n_end
         for name in loss_cfg:
             if name not in L.TERM_INDEX:
                 raise NotImplementedError(f"residual '{name}' has no CUDA implementation (no CPU fallback)")
         pb = L.Problem()
         pb.P, pb.T, pb.J, pb.n_params = P, T, J, lay.n_params
-        pb.p_begin, pb.p_end, pb.owner, pb.lbs_mode = p_begin, p_end, int(owner), lbs_mode
+        pb.n_begin, pb.n_end, pb.owner, pb.lbs_mode = n_begin, n_end, int(owner), lbs_mode
         keep = []
         # ---- camera mode (global_recon_model.py:473-508)
         mode = L.CAM_CONST
@@ -336,7 +336,9 @@ def bind_variables(data, layout, theta):
     for p, d in enumerate(data['person_data'].values()):
         pv = layout.views(theta, p)
         for name in ['traj_local_xy', 'traj_local_heading', 'traj_local_dxy', 'traj_local_dheading', 'traj_local_z',
-                     'traj_local_rot', 'smpl_orient_world_res', 'root_trans_world_res']:
+                     'traj_local_rot', 'smpl_orient_world_res', 'root_trans_world_res', 'world_dheading']:
+            # world_dheading exists once a stage has requested it (global_recon_model.py:624-627); with continue_opt it
+            # arrives already optimised and forward() keeps composing with it (:459-465)
             if name in d:
                 pv[name].copy_(torch.as_tensor(d[name]).to(theta))
                 d[name] = pv[name]

@@ -28,8 +28,6 @@ def tensor_to(x, device):
     """lib/utils/torch_utils.py:101 -- numpy / nested containers -> tensors on `device` (dtype preserved)"""
     if isinstance(x, np.ndarray):
         return torch.tensor(x, device=device)
-    if isinstance(x, (np.floating, np.integer, np.bool_)):
-        return torch.tensor(x, device=device)
     if isinstance(x, torch.Tensor):
         return x.to(device)
     if isinstance(x, dict):
@@ -90,7 +88,7 @@ def rotmats_to_rotvec(mats):
     SciPy projects every float32-accurate input onto SO(3) with one SVD per matrix (12 ms for a 300-frame track); the
     same polar factor U V^T is reached here by two Newton steps R <- (R + R^-T) / 2 written with cross products, then
     the usual largest-diagonal quaternion branch and the rotation-vector scaling (series below 1e-3 rad)."""
-    R = np.asarray(mats, dtype=np.float64).reshape(-1, 3, 3)
+    R0 = R = np.asarray(mats, dtype=np.float64).reshape(-1, 3, 3)
     for _ in range(2):
         a, b, c = R[:, 0], R[:, 1], R[:, 2]                      # rows; cofactor rows are their cross products (explicit:
         cof = np.empty_like(R)                                   # np.cross is several times slower on [n,3] operands)
@@ -104,7 +102,17 @@ def rotmats_to_rotvec(mats):
         cof[:, 2, 1] = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
         cof[:, 2, 2] = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
         det = a[:, 0] * cof[:, 0, 0] + a[:, 1] * cof[:, 0, 1] + a[:, 2] * cof[:, 0, 2]
-        R = 0.5 * (R + cof / det[:, None, None])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            R = 0.5 * (R + cof / det[:, None, None])
+    # two Newton steps reach the polar factor only from a near-orthogonal start (HybrIK's float32 matrices).  Rows that are
+    # not there yet (or improper / singular inputs) go through SciPy's SVD projection like the reference (which also raises
+    # on non-finite input).
+    resid = np.abs(np.einsum('nij,nkj->nik', R, R) - np.eye(3)).reshape(-1, 9).max(axis=1)
+    bad = ~(np.linalg.det(R) > 0) | ~(resid < 1e-9)
+    if bad.any():
+        from scipy.spatial.transform import Rotation
+        R = R.copy()
+        R[bad] = Rotation.from_matrix(R0[bad]).as_matrix()
     d = np.stack([R[:, 0, 0], R[:, 1, 1], R[:, 2, 2], R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]], axis=1)
     choice = d.argmax(axis=1)
     q = np.empty((R.shape[0], 4))
@@ -483,12 +491,10 @@ class GlobalReconOptimizer:
         self._reduce = torch.zeros(self._layout.n_params + NUM_TERMS, device=self.device)
         self._terms = torch.zeros(NUM_TERMS + 1, device=self.device)
         self._stage_key = None
-        P = self._comp.P
-        if self.world > 1:
-            per = (P + self.world - 1) // self.world
-            self._p_range = (min(self.rank * per, P), min((self.rank + 1) * per, P))
-        else:
-            self._p_range = (0, P)
+        # multi-GPU: contiguous shards of the frame-persons n = p*T + t (SMPL + per-frame residuals are independent per
+        # frame-person, so a person may straddle two ranks; P persons on P GPUs gives one person each)
+        N = self._comp.P * self._comp.T
+        self._n_range = (N * self.rank // self.world, N * (self.rank + 1) // self.world)
 
     def _release(self, at_exit=False):
         if getattr(self, '_opt', None):
@@ -565,7 +571,7 @@ class GlobalReconOptimizer:
     def _set_stage(self, data, opt_variables, loss_cfg, stage, reset_adam, begin=False):
         if begin:            # get_parameter side effects happen once per optimize_main, not on every forward
             PB.begin_stage_variables(data, self._layout, self._theta, self._flags, opt_variables)
-        pb = self._comp.compile(self._theta, opt_variables, loss_cfg, stage, p_begin=self._p_range[0], p_end=self._p_range[1],
+        pb = self._comp.compile(self._theta, opt_variables, loss_cfg, stage, n_begin=self._n_range[0], n_end=self._n_range[1],
                                 owner=(self.rank == 0), lbs_mode=0 if self.lbs_mode == 'full' else 1)
         self._pb = pb
         dims = (pb.P, pb.T, pb.J, pb.n_params)
@@ -601,6 +607,20 @@ class GlobalReconOptimizer:
         ociw, tciw = self._read(L.R_ORIENT_CIW, P, T, 3), self._read(L.R_TRANS_CIW, P, T, 3)
         tl = self._read(L.R_TRAJ_LOCAL, P, T, 11)
         jw = self._read(L.R_JOINTS_WORLD, P, T, J, 3)
+        if self.world > 1:
+            # per-frame-person outputs exist only on the rank that evaluated that frame-person: keep the own shard, sum over ranks
+            own = torch.zeros(P * T, device=self.device)
+            own[self._n_range[0]:self._n_range[1]] = 1.0
+            own = own.view(P, T)
+            packed = torch.cat([(x * own.view(P, T, *([1] * (x.dim() - 2)))).reshape(P * T, -1) for x in (kp, ociw, tciw, jw)], dim=1).contiguous()
+            torch.distributed.all_reduce(packed)
+            o = 0
+            outs = []
+            for x in (kp, ociw, tciw, jw):
+                w = x[0, 0].numel()
+                outs.append(packed[:, o:o + w].reshape(x.shape))
+                o += w
+            kp, ociw, tciw, jw = outs
         data['cam_pose'] = G.from34(self._read(L.R_CAM_POSE, T, 12))
         data['cam_pose_inv'] = G.from34(self._read(L.R_CAM_POSE_INV, T, 12))
         for p, d in enumerate(data['person_data'].values()):

@@ -169,7 +169,8 @@ typedef struct glamr_problem {
   int32_t trans_res_all;           /* mode 3: cam_inv_trans_residual has T rows (else one row per empty frame)    */
   int32_t cam_up_first_only;
   int32_t n_params;                /* length of theta / grad / adam state                                         */
-  int32_t p_begin, p_end;          /* persons whose SMPL / per-frame residuals this rank evaluates (multi-GPU)   */
+  int32_t n_begin, n_end;          /* frame-persons n = p*T + t whose SMPL / per-frame residuals this rank evaluates
+                                    * (multi-GPU shard; any contiguous range, a person may straddle two ranks)         */
   int32_t owner;                   /* != 0: this rank also evaluates the replicated terms (camera, regs, rel)    */
   int32_t lbs_mode;                /* 0 full LBS every iteration, 1 rigid fast mode (cached body-frame joints)   */
   int32_t pad_;

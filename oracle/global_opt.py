@@ -43,6 +43,15 @@ def _to_numpy(x):
     return x
 
 
+def cast_floats(x, dtype):
+    """every floating tensor of a nested data dict -> `dtype` (bool / integer tensors and python values untouched)"""
+    if isinstance(x, torch.Tensor):
+        return x.detach().to(dtype) if x.is_floating_point() else x
+    if isinstance(x, dict):
+        return {k: cast_floats(v, dtype) for k, v in x.items()}
+    return x
+
+
 class OracleGlobalRecon:
     """Same constructor/methods as the reference class (global_recon_model.py:23-67,572-589)."""
 
@@ -51,6 +60,7 @@ class OracleGlobalRecon:
         self.specs = s = cfg.grecon_model_specs
         self.log = log
         self.cur_iter = 0
+        self._assets = smpl_assets
         self.smpl = OracleSMPL(smpl_assets)
         self.mt_model = mt_model
         g = s.get
@@ -79,6 +89,13 @@ class OracleGlobalRecon:
                 raise NotImplementedError(f'{flag} is not restated in the oracle')
         if g('heading_type', 'scalar') != 'scalar':
             raise NotImplementedError('heading_type != scalar')
+
+    def to_float64(self, data):
+        """Noise-floor instrument (tests/golden/make_golden.py): continue from the SAME float32 state with every
+        per-iteration formula evaluated in float64 -- forward, residuals, autograd, Adam.  |ref32 - ref64| is then the
+        rounding-noise amplification of the reference itself, the yardstick for |cuda - ref64|."""
+        self.smpl = OracleSMPL(self._assets, dtype=torch.float64)
+        return cast_floats(data, torch.float64)
 
     # ------------------------------------------------------------------ init (global_recon_model.py:76-248)
     def _person_from_estimate(self, est, gt_entry):
@@ -336,7 +353,7 @@ class OracleGlobalRecon:
                     d['root_trans_world'] = d['root_trans_world_base']
                 if 'world_dheading' in d:
                     dh = d['world_dheading']
-                    dq = rt.aa_to_quat(torch.cat([torch.zeros(dh.shape[0], 2), dh], dim=-1))
+                    dq = rt.aa_to_quat(torch.cat([torch.zeros(dh.shape[0], 2, dtype=dh.dtype), dh], dim=-1))
                     d['smpl_orient_world'] = rt.quat_to_aa(rt.quat_mul(dq, rt.aa_to_quat(d['smpl_orient_world_base'])))
                     d['root_trans_world'] = d['root_trans_world_base']
                 if 'world_dxy' in d:
@@ -359,8 +376,9 @@ class OracleGlobalRecon:
             d['smpl_orient_cam_in_world'] = rt.transform_rot(data['cam_pose'], d['smpl_orient_world'])
             d['root_trans_cam_in_world'] = rt.transform_trans(data['cam_pose'], d['root_trans_world'])
             if 'smpl_pose' in d and 'cam_K' in d:
-                joints, _ = self.smpl(d['smpl_orient_world'], d['smpl_pose'].to(torch.float32),
-                                      d['smpl_beta'].to(torch.float32), root_trans=d['root_trans_world'],
+                dt = d['smpl_orient_world'].dtype                           # float32 (reference); float64 in the noise-floor runs
+                joints, _ = self.smpl(d['smpl_orient_world'], d['smpl_pose'].to(dt),
+                                      d['smpl_beta'].to(dt), root_trans=d['root_trans_world'],
                                       root_scale=d['scale'])
                 d['joints_world'] = joints
                 d['kp_2d_pred'] = rt.perspective_projection(rt.transform_trans(data['cam_pose'], joints), d['cam_K'])

@@ -33,7 +33,55 @@ GLOBALOPT_CASES = [
     ('dynamic_multi_p2_t32', 'glamr_dynamic_multi', 2, 32, False, 4),
     ('3dpw_p2_t80_gaps', 'glamr_3dpw', 2, 80, True, 4),
     ('h36m_p1_t48_gaps', 'glamr_h36m', 1, 48, True, 4),
+    # the shapes bench.py measures (BASELINE.json configs[1], the north-star 4 x 300 video, T = 500 of configs[3]) and a
+    # T > 512 track with gaps (more than one chunk of the CTA-wide prefix scans)
+    ('dynamic_p1_t300', 'glamr_dynamic', 1, 300, False, 50),
+    ('static_multi_p4_t300', 'glamr_static_multi', 4, 300, False, 10),
+    ('static_multi_p2_t500', 'glamr_static_multi', 2, 500, False, 5),
+    ('3dpw_p1_t600_gaps', 'glamr_3dpw', 1, 600, True, 4),
 ]
+FINAL_KEYS = ['smpl_orient_world', 'root_trans_world', 'kp_2d_pred', 'traj_local_xy', 'traj_local_dxy', 'traj_local_heading',
+              'traj_local_dheading', 'traj_local_z', 'traj_local_rot', 'world_dheading', 'smpl_orient_cam_in_world',
+              'root_trans_cam_in_world', 'person_transform_world', 'traj_local']
+FINAL_GLOBAL_KEYS = ['cam_pose', 'cam_pose_inv', 'cam_rot_6d', 'cam_trans', 'cam_rot_6d_fix', 'cam_trans_fix',
+                     'cam_inv_rot_residual', 'cam_inv_trans_residual']
+
+
+def float64_trajectory(assets, name, cfg_id, P, T, gaps, niters, rec):
+    """Noise floor of the k-step comparison: the oracle restatement (pinned to the reference by
+    tests/test_oracle_vs_golden.py) continues from the same float32 init state with every per-iteration formula in
+    float64.  |final - final64| of the executed float32 reference is how far rounding noise alone moves the optimiser;
+    the CUDA path is held to a small multiple of it (tests/test_gpu_parity.py)."""
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    from helpers import ReplayMT
+    from glamr_b200.config import Config
+    from oracle.global_opt import OracleGlobalRecon
+    cfg = Config(cfg_id)
+    for st in cfg.opt_stage_specs.values():
+        st['opt_niters'] = niters
+    in_dict = make_in_dict(assets, P, T, seed=0, gaps=gaps, seq_name=name)
+    ora = OracleGlobalRecon(cfg, assets, mt_model=ReplayMT(rec))
+    data = ora.to_float64(ora.init_data(in_dict))
+    out = {}
+    for stage, specs in cfg.opt_stage_specs.items():
+        logs = []
+        ora.optimize_main(data, specs['opt_variables'], specs['opt_lr'], specs['opt_niters'], specs['loss_cfg'], {'stage': stage},
+                          on_iter=lambda it, last, dt: logs.append({k: float(v) for k, v in last['uw'].items()}))
+        if specs.get('reinitialize_cam', False):
+            from oracle import rotations as rt
+            data['cam_pose'][:] = data['cam_pose'][[0]]
+            data['cam_pose_inv'] = rt.inverse_transform(data['cam_pose'])
+        for k in logs[0]:
+            out[f'loss64/{stage}/{k}'] = np.asarray([l[k] for l in logs], np.float64)
+    for k in FINAL_GLOBAL_KEYS:
+        if k in data:
+            out[f'final64/{k}'] = data[k].detach().numpy()
+    for pid, pd in data['person_data'].items():
+        for k in FINAL_KEYS:
+            if k in pd and pd[k] is not None:
+                out[f'final64/{pid}/{k}'] = pd[k].detach().numpy()
+    return out
+
 
 
 def rotation_vectors():
@@ -229,18 +277,16 @@ def globalopt_case(assets, name, cfg_id, P, T, gaps, niters):
             rec[f'mt/{i}/{k}'] = v.numpy()
     for k, v in losses.items():
         rec[f'loss/{k}'] = np.asarray(v, np.float64)
-    for k in ['cam_pose', 'cam_pose_inv', 'cam_rot_6d', 'cam_trans', 'cam_rot_6d_fix', 'cam_trans_fix',
-              'cam_inv_rot_residual', 'cam_inv_trans_residual']:
+    for k in FINAL_GLOBAL_KEYS:
         if k in out:
             rec[f'final/{k}'] = out[k]
     for pid, pd in out['person_data'].items():
-        for k in ['smpl_orient_world', 'root_trans_world', 'kp_2d_pred', 'traj_local_xy', 'traj_local_dxy', 'traj_local_heading',
-                  'traj_local_dheading', 'traj_local_z', 'traj_local_rot', 'world_dheading', 'smpl_orient_cam_in_world',
-                  'root_trans_cam_in_world', 'person_transform_world', 'traj_local']:
+        for k in FINAL_KEYS:
             if k in pd and pd[k] is not None:
                 rec[f'final/{pid}/{k}'] = pd[k]
     rec['meta'] = np.array([P, T, int(gaps), niters])
     rec['cfg_id'] = np.array(cfg_id)
+    rec.update(float64_trajectory(assets, name, cfg_id, P, T, gaps, niters, rec))
     return rec
 
 

@@ -7,6 +7,8 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 GLOBALOPT_CASES = ['dynamic_p1_t40', 'static_p1_t24', 'static_multi_p3_t30', 'dynamic_multi_p2_t32', '3dpw_p2_t80_gaps', 'h36m_p1_t48_gaps']
+# the shapes bench.py measures (+ a T > 512 track): reference goldens with more iterations, see tests/golden/make_golden.py
+BENCH_SHAPE_CASES = ['dynamic_p1_t300', 'static_multi_p4_t300', 'static_multi_p2_t500', '3dpw_p1_t600_gaps']
 
 
 def load_golden(name):

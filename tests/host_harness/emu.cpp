@@ -121,7 +121,7 @@ int glamr_host_emu_backward(EmuHandle* h, const float* theta, float* reduce_buf)
   for (int p = 0; p < pb.P; ++p)
     for (int t = 0; t < pb.T; ++t) {
       const size_t n = (size_t)p * pb.T + t;
-      if (p >= pb.p_begin && p < pb.p_end) frame_residuals(c, p, t, acc);
+      if ((int)n >= pb.n_begin && (int)n < pb.n_end) frame_residuals(c, p, t, acc);
       else {
         for (int k = 0; k < 3; ++k) { c.sc.g_orient[n * 3 + k] = 0; c.sc.g_trans[n * 3 + k] = 0; }
         for (int k = 0; k < 12; ++k) c.sc.g_cam[n * 12 + k] = 0;

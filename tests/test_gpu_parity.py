@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GLOBALOPT_CASES, ReplayMT, case_setup, load_golden
+from helpers import BENCH_SHAPE_CASES, GLOBALOPT_CASES, ReplayMT, case_setup, load_golden
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -136,43 +136,75 @@ def _make(name, smpl_assets, **spec_over):
     return gold, cfg, in_dict, model
 
 
-@pytest.mark.parametrize('name', GLOBALOPT_CASES)
-def test_globalopt_matches_reference_golden(name, smpl_assets):
-    """init state, iteration-0 gradients, per-iteration residual values and final poses vs the executed reference"""
-    from glamr_b200 import lib as L
-    gold, cfg, in_dict, model = _make(name, smpl_assets)
-    data = model.init_data(copy.deepcopy(in_dict))
+EPS32 = 2.0 ** -24
+
+
+def noise_floor_tol(ref32, ref64, c=4.0, ulps=32):
+    """Tolerance of a k-step comparison against the float64 continuation stored in the fixture: `c` times what the executed
+    float32 reference itself deviates from it (max over the tensor), plus `ulps` float32 roundings of the tensor's magnitude
+    (prefix sums over T frames).  Where the optimisation is well conditioned this is ~1e-6..1e-5, far below the 1e-4
+    north-star bound; where Adam amplifies rounding noise (frames without observations) it is as loose as the reference's
+    own float32 arithmetic is -- and no looser."""
+    return c * float(np.abs(ref32 - ref64).max()) + ulps * EPS32 * max(float(np.abs(ref64).max()), 1.0)
+
+
+def _check_init_state(data, gold):
     for p, (pid, pd) in enumerate(data['person_data'].items()):
         np.testing.assert_allclose(pd['kp_2d_pred'].cpu().numpy(), gold[f'init/{pid}/kp_2d_pred'], atol=5e-3, err_msg='init kp')
         np.testing.assert_allclose(pd['smpl_orient_world'].cpu().numpy(), gold[f'init/{pid}/smpl_orient_world'], atol=1e-4)
         np.testing.assert_allclose(pd['root_trans_world'].cpu().numpy(), gold[f'init/{pid}/root_trans_world'], atol=1e-4)
         np.testing.assert_allclose(pd['traj_local_pred'].cpu().numpy(), gold[f'init/{pid}/traj_local_pred'], atol=1e-5)
     np.testing.assert_allclose(data['cam_pose'].cpu().numpy(), gold['init/cam_pose'], atol=1e-5)
+
+
+def _check_trajectory_against_noise_floor(model, data, cfg, gold):
+    """every stage: per-iteration residual values; after the last stage: final variables and poses of ALL frames
+    (observed or not), each against the float64 continuation with the reference's own float32 deviation as yardstick"""
+    from glamr_b200 import lib as L
+    report = {}
     for stage, specs in cfg.opt_stage_specs.items():
         n = specs['opt_niters']
         model.optimize_main(data, specs['opt_variables'], specs['opt_lr'], n, specs['loss_cfg'], {'stage': stage})
+        if specs.get('reinitialize_cam', False):
+            from glamr_b200 import geometry as G
+            data['cam_pose'][:] = data['cam_pose'][[0]]
+            data['cam_pose_inv'] = G.inverse_transform(data['cam_pose'])
         hist = model.loss_history.cpu().numpy()
         for k in specs['loss_cfg']:
-            ref = gold[f'loss/{stage}/{k}']
+            r32, r64 = gold[f'loss/{stage}/{k}'], gold[f'loss64/{stage}/{k}']
             got = hist[:n, L.TERM_INDEX[k]]
-            # iteration 0 is a pure forward on identical variables; later iterations follow Adam steps of
-            # ~lr*sign(g), where zero-gradient directions random-walk on rounding noise in BOTH implementations
-            # (see tests/test_globalopt_host_emu.py), so small terms such as the smoothness monitors drift by a few per cent
-            # (6.8 % after 3 steps in glamr_h36m, whose data terms carry weights of 1e4) ...
-            np.testing.assert_allclose(got[:1], ref[:1], rtol=2e-3, atol=1e-5, err_msg=f'{stage} {k} (iteration 0)')
-            np.testing.assert_allclose(got, ref, rtol=1e-1, atol=1e-4, err_msg=f'{stage} {k}')
-        # ... while the weighted objective, dominated by the data terms, must track the reference closely at every iteration
-        terms = [k for k in specs['loss_cfg'] if not specs['loss_cfg'][k].get('monitor_only', False)]
-        ref_total = sum(specs['loss_cfg'][k]['weight'] * gold[f'loss/{stage}/{k}'] for k in terms)
-        np.testing.assert_allclose(hist[:n, L.NUM_TERMS], ref_total, rtol=3e-2, err_msg=f'{stage} weighted total')
+            # iteration 0 is a pure forward on identical variables
+            np.testing.assert_allclose(got[:1], r64[:1], rtol=2e-4, atol=1e-6, err_msg=f'{stage} {k} (iteration 0)')
+            tol = 4.0 * np.abs(r32 - r64).max() + 2e-4 * np.abs(r64).max() + 1e-6
+            err = np.abs(got - r64).max()
+            assert err <= tol, f'{stage} {k}: |cuda-ref64| {err:.3e} > {tol:.3e} (|ref32-ref64| {np.abs(r32 - r64).max():.3e})'
+    checks = [('cam_pose', data['cam_pose'].cpu().numpy())]
     for pid, pd in data['person_data'].items():
-        # frames without observations sit on ill-conditioned 6d rotations (the random-init prior emits |a1| << 1) where the
-        # Adam rounding-noise walk of traj_local_rot is amplified; compare the observed frames
-        vis = gold[f'init/{pid}/vis_frames']
-        for k, tol in [('smpl_orient_world', 2e-3), ('root_trans_world', 2e-3)]:
-            np.testing.assert_allclose(pd[k].cpu().numpy()[vis], gold[f'final/{pid}/{k}'][vis], atol=tol, err_msg=f'final {pid} {k}')
-        np.testing.assert_allclose(pd['traj_local_xy'].cpu().numpy(), gold[f'final/{pid}/traj_local_xy'], atol=1e-3)
-    np.testing.assert_allclose(data['cam_pose'].cpu().numpy(), gold['final/cam_pose'], atol=2e-3)
+        for k in ['smpl_orient_world', 'root_trans_world', 'traj_local_xy', 'traj_local_dxy', 'traj_local_z', 'traj_local_rot',
+                  'traj_local_heading', 'world_dheading', 'kp_2d_pred']:
+            if k in pd and f'final64/{pid}/{k}' in gold:
+                checks.append((f'{pid}/{k}', pd[k].cpu().numpy()))
+    for key, got in checks:
+        r32, r64 = gold[f'final/{key}'], gold[f'final64/{key}']
+        tol = noise_floor_tol(r32, r64, ulps=32 if 'kp_2d_pred' not in key else 256)
+        err = float(np.abs(got.reshape(r64.shape) - r64).max())
+        report[key] = (err, float(np.abs(r32 - r64).max()))
+        assert err <= tol, f'final {key}: |cuda-ref64| {err:.3e} > {tol:.3e} (|ref32-ref64| {np.abs(r32 - r64).max():.3e})'
+    return report
+
+
+@pytest.mark.parametrize('name', GLOBALOPT_CASES + BENCH_SHAPE_CASES)
+def test_globalopt_matches_reference_golden(name, smpl_assets):
+    """init state, per-iteration residual values and the final state of every frame vs the executed reference.  The small
+    cases cover every camera mode / config family; the BENCH_SHAPE cases are the shapes bench.py times (1 x 300
+    glamr_dynamic with 50 iterations, the 4 x 300 glamr_static_multi north-star video, T = 500, and a T = 600 track with
+    gaps that needs two chunks of the CTA-wide prefix scans)."""
+    gold, cfg, in_dict, model = _make(name, smpl_assets)
+    data = model.init_data(copy.deepcopy(in_dict))
+    _check_init_state(data, gold)
+    report = _check_trajectory_against_noise_floor(model, data, cfg, gold)
+    worst = max(report.items(), key=lambda kv: kv[1][0] / max(kv[1][1], 1e-9))
+    print(f'{name}: worst ratio |cuda-ref64| / |ref32-ref64| at {worst[0]}: {worst[1][0]:.2e} / {worst[1][1]:.2e}')
 
 
 @pytest.mark.parametrize('name', ['dynamic_p1_t40', 'static_multi_p3_t30', '3dpw_p2_t80_gaps'])

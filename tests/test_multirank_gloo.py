@@ -1,6 +1,6 @@
 """N>1 path on CPU: persons sharded over 2 ranks (gloo), one all-reduce of the packed [gradient | term sums] buffer,
 must equal the single-rank result.  Uses the host-compiled frame functions (tests/host_harness) and the same
-problem compiler / sharding fields (p_begin, p_end, owner) the CUDA path uses."""
+problem compiler / sharding fields (n_begin, n_end, owner) the CUDA path uses."""
 import copy
 import os
 import socket
@@ -45,8 +45,8 @@ def _worker(rank, world, port, name, ret):
         if mode == 'single':
             run.set_stage(specs['opt_variables'], specs['loss_cfg'], stage)
         else:
-            per = (P + world - 1) // world
-            run.set_stage(specs['opt_variables'], specs['loss_cfg'], stage, p_begin=min(rank * per, P), p_end=min((rank + 1) * per, P),
+            N = P * run.comp.T           # contiguous frame-person ranges; with P = 3 a person straddles the two ranks
+            run.set_stage(specs['opt_variables'], specs['loss_cfg'], stage, n_begin=N * rank // world, n_end=N * (rank + 1) // world,
                           owner=(rank == 0))
         for it in range(3):
             run.backward()

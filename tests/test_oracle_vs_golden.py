@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GLOBALOPT_CASES, ReplayMT, case_setup, load_golden
+from helpers import BENCH_SHAPE_CASES, GLOBALOPT_CASES, ReplayMT, case_setup, load_golden
 from oracle import rotations as rt
 from oracle import traj_codec as tc
 from oracle.global_opt import OracleGlobalRecon
@@ -115,6 +115,35 @@ def test_globalopt_trajectory_matches_reference(name, smpl_assets):
             if f'final/{pid}/{k}' in gold:
                 np.testing.assert_allclose(pd[k].detach().numpy(), gold[f'final/{pid}/{k}'], atol=1e-4, err_msg=f'final {pid} {k}')
     np.testing.assert_allclose(data['cam_pose'].numpy(), gold['final/cam_pose'], atol=1e-4)
+
+
+@pytest.mark.parametrize('name', BENCH_SHAPE_CASES)
+def test_globalopt_bench_shapes_match_reference(name, smpl_assets):
+    """the oracle at the shapes bench.py times (T = 300 / 500 / 600, up to 4 persons, up to 50 iterations): init state and the
+    first iterations tightly; the whole trajectory and the final state within the reference's own float32-vs-float64 deviation"""
+    gold, cfg, in_dict = case_setup(name, smpl_assets)
+    model = OracleGlobalRecon(cfg, smpl_assets, mt_model=ReplayMT(gold))
+    data = model.init_data(in_dict)
+    for pid, pd in data['person_data'].items():
+        for k in ['kp_2d_pred', 'smpl_orient_world', 'root_trans_world', 'traj_local_pred']:
+            np.testing.assert_allclose(pd[k].numpy(), gold[f'init/{pid}/{k}'], atol=1e-3 if k == 'kp_2d_pred' else 1e-5, err_msg=f'init {pid} {k}')
+    for stage, specs in cfg.opt_stage_specs.items():
+        logs = []
+        model.optimize_main(data, specs['opt_variables'], specs['opt_lr'], specs['opt_niters'], specs['loss_cfg'], {'stage': stage},
+                            on_iter=lambda it, last, dt: logs.append({k: float(v) for k, v in last['uw'].items()}))
+        for k in logs[0]:
+            r32, r64 = gold[f'loss/{stage}/{k}'], gold[f'loss64/{stage}/{k}']
+            got = np.array([l[k] for l in logs])
+            if stage == list(cfg.opt_stage_specs)[0]:
+                np.testing.assert_allclose(got[:2], r32[:2], rtol=2e-4, atol=1e-6, err_msg=f'{stage} {k} first iterations')
+            tol = 4.0 * np.abs(r32 - r64).max() + 2e-4 * np.abs(r64).max() + 1e-6
+            assert np.abs(got - r64).max() <= tol, f'{stage} {k}'
+    eps = 2.0 ** -24
+    for pid, pd in data['person_data'].items():
+        for k in ['smpl_orient_world', 'root_trans_world', 'traj_local_xy', 'traj_local_rot']:
+            r32, r64 = gold[f'final/{pid}/{k}'], gold[f'final64/{pid}/{k}']
+            tol = 4.0 * np.abs(r32 - r64).max() + 32 * eps * max(np.abs(r64).max(), 1.0)
+            assert np.abs(pd[k].detach().numpy() - r64).max() <= tol, f'final {pid} {k}'
 
 
 def test_camera_only_terms_match_reference_functions():
