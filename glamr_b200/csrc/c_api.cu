@@ -77,9 +77,38 @@ __global__ void __launch_bounds__(kScanThreads) traj_local2global_kernel(int T, 
   }
 }
 
+// Register-resident FFMA loop: what the FP32 pipe of this GPU sustains at its current clocks (bench.py quotes the LBS kernel,
+// FP32-FMA bound by construction, against this measured number instead of a data-sheet peak).
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* __restrict__ out, int iters, float b, float c) {
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = (float)(threadIdx.x + j) * 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], b, c);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += a[j];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace glamr
 
 using namespace glamr;
+
+extern "C" int glamr_fp32_probe(int iters, float* scratch, size_t scratch_floats, double* flops, void* stream) {
+  if (iters <= 0 || !scratch || !flops) return GLAMR_EINVAL;
+  int dev = 0, sms = 0;
+  GLAMR_CUDA_TRY(cudaGetDevice(&dev));
+  GLAMR_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = sms * 8;                       // 8 x 256 threads = 64 warps per SM
+  if (scratch_floats < (size_t)grid * 256) return GLAMR_ENOSPACE;
+  fp32_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999f, 1e-3f);
+  GLAMR_LAUNCH_CHECK();
+  *flops = (double)grid * 256.0 * (double)iters * 16.0 * 2.0;
+  return GLAMR_OK;
+}
 
 extern "C" int glamr_rowop_fwd(int op, int n, const float* in0, const float* in1, float* out, void* stream) {
   int d0, d1, dout;

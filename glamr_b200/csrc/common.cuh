@@ -19,6 +19,14 @@
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+// Work-skipping experiment switches (tools/*_exp.py) exist only in a -DGLAMR_EXPERIMENT build; the release library that
+// bench.py and the tests load has them compiled out.
+#ifdef GLAMR_EXPERIMENT
+#define GLAMR_DBG(x) (x)
+#else
+#define GLAMR_DBG(x) 0
+#endif
+
 namespace glamr {
 
 constexpr int kV = GLAMR_NUM_VERTS;          // 6890

@@ -500,6 +500,14 @@ extern "C" int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* pb,
 
 extern "C" size_t glamr_opt_reduce_count(const glamr_opt_t* st) { return st ? (size_t)st->pb.n_params + GLAMR_NUM_TERMS : 0; }
 
+extern "C" int glamr_opt_launch_count(const glamr_opt_t* st) {
+  if (!st) return GLAMR_EINVAL;
+  const bool from_persons = st->pb.cam_mode == GLAMR_CAM_FROM_PERSONS;
+  const bool has_frames = st->pb.n_end > st->pb.n_begin;
+  // traj/cam forward [+ cam_forward] + pose_prep + lbs + residuals [+ camera backward + scatter] + traj/cam backward + apply
+  return 1 + (from_persons ? 1 : 0) + (has_frames ? 2 : 0) + 1 + (from_persons ? 2 : 0) + 1 + 1;
+}
+
 #define GLAMR_MARK() do { if (st->timing == 2 && st->n_ev < 24) GLAMR_CUDA_TRY(cudaEventRecord(st->ev[st->n_ev++], s)); } while (0)
 
 static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream, bool use_peers) {

@@ -119,7 +119,9 @@ __device__ __forceinline__ float4 split_tf32_4(const float4 v, float4& lo) {
   return hi;
 }
 
-__device__ int g_tc_dbg = 0;   // experiment switches (tools/tc_gemm_exp.py, env GLAMR_TC_DEBUG); 0 in production
+#ifdef GLAMR_EXPERIMENT
+__device__ int g_tc_dbg = 0;   // experiment switches (tools/tc_gemm_exp.py, env GLAMR_TC_DEBUG); not in the release build
+#endif
 constexpr int kTcThreads = 256;
 constexpr int kTcStages = 2;
 template <int NT>
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
     mbar_fence_init();
   }
   const int nk = (K + TCK - 1) / TCK;
-  const int dbg = g_tc_dbg;
+  const int dbg = GLAMR_DBG(g_tc_dbg);
   TcRegs<NT> regs;
   tc_load_tiles<NT, VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, 0);
   tc_store_tiles<NT>(stage0, tid, regs);
@@ -356,10 +358,12 @@ static int gemm(cudaStream_t s, int M, int N, int K, const float* X, int ldx, co
   if (g_gemm_mode == 1) {
     static int ntile = -1;     // GLAMR_TC_NTILE = 32 | 128 forces one tile shape (experiments); default: by problem height
     if (ntile < 0) {
+#ifdef GLAMR_EXPERIMENT
       if (const char* e = getenv("GLAMR_TC_DEBUG")) {
         const int v = atoi(e);
         GLAMR_CUDA_TRY(cudaMemcpyToSymbol(g_tc_dbg, &v, sizeof(int)));
       }
+#endif
       const char* t = getenv("GLAMR_TC_NTILE");
       ntile = t ? atoi(t) : 0;
     }

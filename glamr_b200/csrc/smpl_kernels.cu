@@ -244,7 +244,7 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
     mbar_wait(&full[s], (c / kStages) & 1);
     const float4* P = reinterpret_cast<const float4*>(PDs + s * kChunkFloats + 12 * lane);
     const float4* F = reinterpret_cast<const float4*>(pfs + s * kPfChunkFloats + wf);
-    if (!(dbg & 1))
+    if (!(GLAMR_DBG(dbg) & 1))
 #pragma unroll
     for (int k = 0; k < kChunkK; ++k) {
       const float4 p0 = P[k * (kTileCols / 4) + 0], p1 = P[k * (kTileCols / 4) + 1], p2 = P[k * (kTileCols / 4) + 2];
@@ -286,7 +286,7 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
   const int n = f0 + fr;
   const bool n_ok = n < n_end;
   const int vbase = (tid >> 5) * 32;
-  if (!(dbg & 2)) {
+  if (!(GLAMR_DBG(dbg) & 2)) {
     if (KREG > 0) {
       const int gvl = min(vtile * kVTile + vbase + lane, kVPad - 1);
       const float4 my_w = *reinterpret_cast<const float4*>(m.skin_w + (size_t)gvl * 4);
@@ -445,8 +445,10 @@ int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, con
   if (!stages) {
     const char* e = getenv("GLAMR_LBS_STAGES");
     stages = (e && atoi(e) == 4) ? 4 : 3;
-    const char* d = getenv("GLAMR_LBS_DEBUG");      // measurement aid only: bit0 skips the FMA loop, bit1 the skinning phase
+#ifdef GLAMR_EXPERIMENT
+    const char* d = getenv("GLAMR_LBS_DEBUG");      // experiment build only: bit0 skips the FMA loop, bit1 the skinning phase
     dbg = d ? atoi(d) : 0;
+#endif
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbs_smem_bytes(3)));
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbs_smem_bytes(3)));
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbs_smem_bytes(4)));

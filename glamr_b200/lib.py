@@ -49,7 +49,7 @@ class Person(ctypes.Structure):
 class Problem(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ['P', 'T', 'J', 'cam_mode', 'off_cam_rot', 'off_cam_trans', 'use_world_res', 'has_world_dheading',
-                 'trans_res_all', 'cam_up_first_only', 'n_params', 'n_begin', 'n_end', 'owner', 'lbs_mode', 'pad_']] + \
+                 'trans_res_all', 'cam_up_first_only', 'n_params', 'n_begin', 'n_end', 'owner', 'pad0_', 'pad_']] + \
                [('cam_up_first_weight', ctypes.c_float), ('rel_trans_weight', ctypes.c_float),
                 ('term_weight', ctypes.c_float * NUM_TERMS), ('term_norm', ctypes.c_float * NUM_TERMS),
                 ('term_enabled', ctypes.c_int32 * NUM_TERMS), ('term_monitor', ctypes.c_int32 * NUM_TERMS)] + \
@@ -101,6 +101,7 @@ def load():
     lib.glamr_sizeof_problem.restype = ctypes.c_size_t
     lib.glamr_opt_reduce_count.restype = ctypes.c_size_t
     lib.glamr_opt_peer_bytes.restype = ctypes.c_size_t
+    lib.glamr_fp32_probe.argtypes = [ctypes.c_int, _vp, ctypes.c_size_t, _vp, _vp]
     lib.glamr_peer_alloc.argtypes = [ctypes.c_size_t, _vp, _vp]
     lib.glamr_peer_open.argtypes = [_vp, _vp]
     lib.glamr_peer_close.argtypes = [_vp]

@@ -171,7 +171,7 @@ class StageCompiler:
             norms['cam_traj_trans'] = nvis
         return kp_w, kp_dm, ctr_w, ctt_w, norms
 
-    def compile(self, theta, opt_variables, loss_cfg, stage, n_begin=0, n_end=None, owner=True, lbs_mode=0):
+    def compile(self, theta, opt_variables, loss_cfg, stage, n_begin=0, n_end=None, owner=True):
         data, lay, fl, dev, P, T, J = self.data, self.layout, self.flags, self.device, self.P, self.T, self.J
         n_end = P * T if n_end is None else n_end
         for name in loss_cfg:
@@ -179,7 +179,7 @@ class StageCompiler:
                 raise NotImplementedError(f"residual '{name}' has no CUDA implementation (no CPU fallback)")
         pb = L.Problem()
         pb.P, pb.T, pb.J, pb.n_params = P, T, J, lay.n_params
-        pb.n_begin, pb.n_end, pb.owner, pb.lbs_mode = n_begin, n_end, int(owner), lbs_mode
+        pb.n_begin, pb.n_end, pb.owner = n_begin, n_end, int(owner)
         keep = []
         # ---- camera mode (global_recon_model.py:473-508)
         mode = L.CAM_CONST

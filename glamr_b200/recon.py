@@ -187,7 +187,6 @@ class GlobalReconOptimizer:
         if not self.flag_opt_traj:
             raise NotImplementedError('flag_opt_traj=false is not implemented in the CUDA path')
         self.rank, self.world = dist if dist is not None else (0, 1)
-        self.lbs_mode = g('lbs_mode', 'full')
         self.log_interval = g('log_interval', 1)
         self.use_cuda_graph = g('use_cuda_graph', True)
         self.mt_cfg = None
@@ -572,7 +571,7 @@ class GlobalReconOptimizer:
         if begin:            # get_parameter side effects happen once per optimize_main, not on every forward
             PB.begin_stage_variables(data, self._layout, self._theta, self._flags, opt_variables)
         pb = self._comp.compile(self._theta, opt_variables, loss_cfg, stage, n_begin=self._n_range[0], n_end=self._n_range[1],
-                                owner=(self.rank == 0), lbs_mode=0 if self.lbs_mode == 'full' else 1)
+                                owner=(self.rank == 0))
         self._pb = pb
         dims = (pb.P, pb.T, pb.J, pb.n_params)
         if self._opt is not None and dims != getattr(self, '_opt_dims', None):
@@ -592,6 +591,10 @@ class GlobalReconOptimizer:
         L.check(self._lib.glamr_opt_backward(self._opt, L.ptr(self._theta), L.ptr(self._reduce), L.stream_ptr()), 'glamr_opt_backward')
         if self.world > 1:
             torch.distributed.all_reduce(self._reduce)        # the one collective of the path: packed gradient + term sums
+
+    def launches_per_iteration(self):
+        """kernels of the CUDA library launched per optimiser iteration for the current stage (excludes the NCCL kernel)"""
+        return int(self._lib.glamr_opt_launch_count(self._opt))
 
     def _read(self, what, *shape):
         p, n = ctypes.c_void_p(), ctypes.c_size_t()

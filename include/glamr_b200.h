@@ -35,6 +35,10 @@ extern "C" {
 int glamr_version(void);
 /* number of SMs / device ordinal the library sees for the current context (for grid sizing diagnostics) */
 int glamr_device_sm_count(void);
+/* Measurement aid: launches a register-resident FFMA loop (8 CTAs x 256 threads per SM, 16 independent chains, `iters`
+ * rounds) on `stream`; *flops (HOST pointer) receives the flop count of the launch.  The caller times it with events: the
+ * FP32 throughput this GPU sustains at its present clocks (bench.py's roofline.fp32.peak).  scratch: >= 8*256*SMs floats. */
+int glamr_fp32_probe(int iters, float* scratch, size_t scratch_floats, double* flops, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * SMPL body model  --  stands behind lib/models/smpl.py:274-343 (class SMPL: forward, get_joints) and the
@@ -172,8 +176,7 @@ typedef struct glamr_problem {
   int32_t n_begin, n_end;          /* frame-persons n = p*T + t whose SMPL / per-frame residuals this rank evaluates
                                     * (multi-GPU shard; any contiguous range, a person may straddle two ranks)         */
   int32_t owner;                   /* != 0: this rank also evaluates the replicated terms (camera, regs, rel)    */
-  int32_t lbs_mode;                /* 0 full LBS every iteration, 1 rigid fast mode (cached body-frame joints)   */
-  int32_t pad_;
+  int32_t pad0_, pad_;             /* (every iteration evaluates the full LBS; there is no reduced mode)          */
   float cam_up_first_weight;
   float rel_trans_weight;
   float term_weight[GLAMR_NUM_TERMS];   /* YAML weight, 0 if the term is absent                                  */
@@ -209,6 +212,8 @@ int glamr_opt_destroy(glamr_opt_t* st);
 int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* problem, int reset_adam, void* stream);
 /* length (floats) of the caller-owned reduce buffer: [grad (n_params) | un-normalised term sums (GLAMR_NUM_TERMS)] */
 size_t glamr_opt_reduce_count(const glamr_opt_t* st);
+/* kernels one glamr_opt_backward + glamr_opt_apply pair launches for the current problem (bench.py: gpu_launches) */
+int glamr_opt_launch_count(const glamr_opt_t* st);
 
 /* forward (trajectory, camera, SMPL, projection) + residuals + analytic backward for the current theta, leaving
  * [grad | term sums] of THIS rank's share in reduce_buf.  With several GPUs the caller sums reduce_buf over ranks
@@ -251,8 +256,7 @@ enum glamr_read {
   GLAMR_R_CAM_POSE = 7,        /* [T,12]    world->cam 3x4               */
   GLAMR_R_CAM_POSE_INV = 8,    /* [T,12]                                 */
   GLAMR_R_JOINTS_WORLD = 9,    /* [P,T,J,3]                              */
-  GLAMR_R_TRAJ_LOCAL = 10,     /* [P,T,11]  traj_local (rows of the exist range, others 0) */
-  GLAMR_R_SMPL_A = 11          /* [P,T,24,12] relative joint transforms of the last SMPL evaluation */
+  GLAMR_R_TRAJ_LOCAL = 10      /* [P,T,11]  traj_local (rows of the exist range, others 0) */
 };
 /* ---- multi-GPU without a library collective: gradient reduction over NVLink peer memory --------------------------
  * One process per GPU.  Every rank allocates one buffer (glamr_peer_alloc; size glamr_opt_peer_bytes), ships its

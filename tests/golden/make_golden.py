@@ -220,6 +220,19 @@ def nets_vectors():
             out[f'{tag}/in/{k}'] = v.numpy()
         for k in ['infer_out_body_pose', 'infer_out_local_traj_tp', 'infer_out_orient', 'infer_out_trans', 'infer_out_pose']:
             out[f'{tag}/{k}'] = res[k].detach().numpy()
+    # BASELINE.json configs[2]: batch 64 x 120 frames, frames 40-69 masked.  Inputs are regenerated from the seed by
+    # c3_prior_inputs() (shared with the GPU test); stored: four whole sequences and per-sequence sums of all 64.
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    from helpers import C3_ROWS, c3_prior_inputs
+    batch = c3_prior_inputs()
+    res = mt.inference({k: v.clone() for k, v in batch.items()}, sample_num=1)
+    sel = C3_ROWS
+    for k, bdim in [('infer_out_body_pose', 0), ('infer_out_local_traj_tp', 1), ('infer_out_orient', 0), ('infer_out_trans', 0)]:
+        v = res[k].detach()
+        out[f'c3_b64_t120/{k}'] = v.index_select(bdim, torch.tensor(sel)).numpy()
+        red = [d for d in range(v.dim()) if d != bdim]
+        out[f'c3_b64_t120/{k}/sum'] = v.double().sum(dim=red).numpy()
+        out[f'c3_b64_t120/{k}/abs_sum'] = v.double().abs().sum(dim=red).numpy()
     return out
 
 

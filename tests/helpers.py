@@ -46,4 +46,19 @@ def case_setup(name, smpl_assets):
     return gold, cfg, in_dict
 
 
+C3_ROWS = [0, 5, 37, 63]
+
+
+def c3_prior_inputs():
+    """seeded inputs of the C3-shape prior run (BASELINE.json configs[2]: 64 sequences x 120 frames, frames 40-69
+    invisible; one motion latent per window and one trajectory latent shared by the batch, injected through the reference's
+    in_motion_latent / in_traj_latent).  Shared by tests/golden/make_golden.py (reference run) and the parity tests."""
+    g = torch.Generator().manual_seed(64)
+    pose = torch.randn(64, 120, 69, generator=g) * 0.3
+    mask = torch.ones(64, 120)
+    mask[:, 40:70] = 0
+    return {'in_body_pose': pose * mask[..., None], 'frame_mask': mask, 'in_motion_latent': torch.randn(4, 128, generator=g),
+            'in_traj_latent': torch.randn(1, 128, generator=g)}
+
+
 from glamr_b200.synthetic import LatentInjector  # noqa: E402,F401  (re-exported for the tests)

@@ -210,9 +210,44 @@ def test_globalopt_matches_reference_golden(name, smpl_assets):
 @pytest.mark.parametrize('name', ['dynamic_p1_t40', 'static_multi_p3_t30', '3dpw_p2_t80_gaps'])
 def test_globalopt_gradients_match_oracle_autograd(name, smpl_assets):
     """first closure of every stage: every variable's gradient vs torch autograd through the full-LBS oracle"""
+    _check_gradients(name, smpl_assets)
+
+
+def _extra_terms_dynamic(cfg):
+    """residuals the registry offers but no shipped config enables (loss_func.py:60-73,94-103,135-144,175-186,216-218),
+    switched on next to the shipped ones: per-frame camera variables"""
+    for st in cfg.opt_stage_specs.values():
+        st['opt_variables'] = list(st['opt_variables']) + ['local_dheading', 'local_dxy', 'local_z']
+        st['loss_cfg'].update({'cam_rot_smoothness': {'weight': 2.0}, 'cam_trans_smoothness': {'weight': 3.0}, 'cam_depth_smoothness': {'weight': 1.5},
+                               'cam_traj_trans': {'weight': 4.0, 'first_frame_weight': 2.0}, 'traj_trans_smoothness': {'weight': 0.7},
+                               'local_traj_dheading_reg': {'weight': 5.0}})
+
+
+def _extra_terms_world_res(cfg):
+    """traj_rot_res / traj_trans_res (loss_func.py:204-209) need the 'world_res' variables (global_recon_model.py:452-454,
+    :609-611); world_dheading would override them (:459-465), so it is dropped from the variable list"""
+    for st in cfg.opt_stage_specs.values():
+        st['opt_variables'] = [v for v in st['opt_variables'] if v != 'world_dheading'] + ['world_res']
+        st['loss_cfg'].update({'traj_rot_res': {'weight': 3.0}, 'traj_trans_res': {'weight': 2.0}, 'cam_traj_trans': {'weight': 1.0},
+                               'traj_trans_smoothness': {'weight': 0.5}, 'cam_depth_smoothness': {'weight': 1.0}})
+
+
+@pytest.mark.parametrize('name,mutate', [('dynamic_p1_t40', _extra_terms_dynamic), ('static_multi_p3_t30', _extra_terms_world_res),
+                                         ('3dpw_p2_t80_gaps', _extra_terms_world_res)])
+def test_unshipped_residual_terms_match_oracle_autograd(name, mutate, smpl_assets):
+    """the 8 registered-but-unshipped residuals on the GPU: values and every variable's gradient vs the oracle's autograd,
+    then the stage's Adam steps in both (so the second stage starts from a moved state)"""
+    _check_gradients(name, smpl_assets, mutate=mutate)
+
+
+def _check_gradients(name, smpl_assets, mutate=None):
     from glamr_b200 import lib as L
+    from glamr_b200.recon import GlobalReconOptimizer
     from oracle.global_opt import OracleGlobalRecon
-    gold, cfg, in_dict, model = _make(name, smpl_assets)
+    gold, cfg, in_dict = case_setup(name, smpl_assets)
+    if mutate is not None:
+        mutate(cfg)
+    model = GlobalReconOptimizer(cfg, torch.device(DEV), None, smpl=smpl_assets, mt_model=ReplayMT(gold, DEV))
     data = model.init_data(copy.deepcopy(in_dict))
     ora = OracleGlobalRecon(copy.deepcopy(cfg), smpl_assets, mt_model=ReplayMT(gold))
     data_o = ora.init_data(copy.deepcopy(in_dict))
@@ -227,6 +262,13 @@ def test_globalopt_gradients_match_oracle_autograd(name, smpl_assets):
         model._cur_vars, model._cur_stage = specs['opt_variables'], stage
         model._set_stage(data, specs['opt_variables'], specs['loss_cfg'], stage, reset_adam=True, begin=True)
         model._backward()
+        # un-normalised term sums ride behind the gradient in the reduce buffer: compare every enabled term's value
+        with torch.cuda.device(DEV):
+            L.check(model._lib.glamr_opt_losses(model._opt, L.ptr(model._reduce), L.ptr(model._terms), L.stream_ptr()), 'glamr_opt_losses')
+        terms = model._terms.cpu().numpy()
+        for k, v in uw.items():
+            got, ref = float(terms[L.TERM_INDEX[k]]), float(v)
+            assert abs(got - ref) <= 3e-4 * max(abs(ref), 1e-3) + 1e-7, f'{stage} term {k}: {got} vs {ref}'
         grad = model._reduce[:model._layout.n_params].cpu()
         lay = model._layout
         gv = lay.views(grad)
@@ -240,6 +282,8 @@ def test_globalopt_gradients_match_oracle_autograd(name, smpl_assets):
         for p in range(len(data['person_data'])):
             pv = lay.views(grad, p)
             for key in specs['opt_variables']:
+                if key == 'world_res':
+                    order += [pv['smpl_orient_world_res'], pv['root_trans_world_res']]
                 if 'local' in key:
                     order.append(pv[f'traj_{key}'])
             if 'world_dheading' in specs['opt_variables']:
@@ -253,9 +297,16 @@ def test_globalopt_gradients_match_oracle_autograd(name, smpl_assets):
             assert err < 5e-4, f'{stage} param {i}: rel err {err:.2e}'
         for p_ in params:
             p_.requires_grad_(False)
-        # advance both by the stage so the next stage starts from comparable states
-        ora.optimize_main(data_o, specs['opt_variables'], specs['opt_lr'], specs['opt_niters'], specs['loss_cfg'], {'stage': stage})
+        # advance by the stage on the GPU and hand the resulting variables to the oracle: the next stage's closure is then
+        # evaluated on IDENTICAL variables in both (two independent Adam runs drift apart on the ill-conditioned cases)
         model.optimize_main(data, specs['opt_variables'], specs['opt_lr'], specs['opt_niters'], specs['loss_cfg'], {'stage': stage})
+        for pd, po in zip(data['person_data'].values(), data_o['person_data'].values()):
+            for k in ['traj_local_xy', 'traj_local_dxy', 'traj_local_heading', 'traj_local_dheading', 'traj_local_z', 'traj_local_rot',
+                      'smpl_orient_world_res', 'root_trans_world_res', 'world_dheading']:
+                if k in pd:
+                    po[k] = pd[k].detach().cpu().clone()
+        for k in ['cam_pose', 'cam_pose_inv', 'cam_inv_rot_residual', 'cam_inv_trans_residual']:
+            data_o[k] = data[k].detach().cpu().clone()
 
 
 def test_optimize_output_layout_and_oracle_parity(smpl_assets):
@@ -335,6 +386,22 @@ def test_prior_inference_matches_reference_golden(tag, cuda_prior):
         assert got.shape == ref.shape
         np.testing.assert_allclose(rt.aa_to_rotmat(got[..., :3]).numpy(), rt.aa_to_rotmat(ref[..., :3]).numpy(), atol=acc_tol, err_msg=f'{tag} {k}')
         np.testing.assert_allclose(got[..., 3:].numpy(), ref[..., 3:].numpy(), atol=1e-4, err_msg=f'{tag} {k} body')
+
+
+def test_prior_c3_shape_matches_reference_golden(cuda_prior):
+    """BASELINE.json configs[2] (64 sequences x 120 frames, frames 40-69 masked) vs the executed reference networks: four whole
+    sequences element-wise, all 64 through per-sequence sums"""
+    from helpers import C3_ROWS, c3_prior_inputs
+    g = load_golden('nets')
+    out = cuda_prior.inference({k: v.to(DEV) for k, v in c3_prior_inputs().items()}, sample_num=1)
+    sel = torch.tensor(C3_ROWS, device=DEV)
+    for k, bdim, tol in [('infer_out_body_pose', 0, 1e-4), ('infer_out_local_traj_tp', 1, 1e-4), ('infer_out_trans', 0, 5e-4 + 2e-5 * 120)]:
+        v = out[k]
+        np.testing.assert_allclose(v.index_select(bdim, sel).cpu().numpy(), g[f'c3_b64_t120/{k}'], atol=tol, err_msg=k)
+        red = [d for d in range(v.dim()) if d != bdim]
+        n_el = v.numel() // v.shape[bdim]
+        np.testing.assert_allclose(v.double().sum(dim=red).cpu().numpy(), g[f'c3_b64_t120/{k}/sum'], atol=tol * n_el ** 0.5 * 4, err_msg=k + ' sum')
+        np.testing.assert_allclose(v.double().abs().sum(dim=red).cpu().numpy(), g[f'c3_b64_t120/{k}/abs_sum'], rtol=1e-4, err_msg=k + ' abs sum')
 
 
 def test_prior_batch_consistency(cuda_prior):

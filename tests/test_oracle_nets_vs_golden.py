@@ -26,3 +26,15 @@ def test_motion_traj_inference_matches_reference(tag, joint_model):
     for k, tol in [('infer_out_body_pose', 2e-5), ('infer_out_local_traj_tp', 2e-5), ('infer_out_orient', 1e-4), ('infer_out_trans', 1e-4),
                    ('infer_out_pose', 1e-4)]:
         np.testing.assert_allclose(out[k].numpy(), g[f'{tag}/{k}'], atol=tol, err_msg=f'{tag} {k}')
+
+
+def test_c3_shape_matches_reference(joint_model):
+    """BASELINE.json configs[2] shape: 64 x 120 with frames 40-69 masked"""
+    from helpers import C3_ROWS, c3_prior_inputs
+    g = load_golden('nets')
+    out = joint_model.inference(c3_prior_inputs(), sample_num=1)
+    sel = torch.tensor(C3_ROWS)
+    for k, bdim, tol in [('infer_out_body_pose', 0, 2e-5), ('infer_out_local_traj_tp', 1, 2e-5), ('infer_out_trans', 0, 1e-4), ('infer_out_orient', 0, 1e-4)]:
+        np.testing.assert_allclose(out[k].index_select(bdim, sel).numpy(), g[f'c3_b64_t120/{k}'], atol=tol, err_msg=k)
+        red = [d for d in range(out[k].dim()) if d != bdim]
+        np.testing.assert_allclose(out[k].double().abs().sum(dim=red).numpy(), g[f'c3_b64_t120/{k}/abs_sum'], rtol=1e-5, err_msg=k)
