@@ -43,7 +43,7 @@ REF_BUDGET_S = float(os.environ.get('GLAMR_REF_BUDGET_S', 150.0))   # wall-clock
 NCU_LBS_DRAM_BYTES = {300: 18942208}
 # switches that change what the library executes: the bench refuses to run with any of them set
 FORBIDDEN_ENV = ['GLAMR_LBS_DEBUG', 'GLAMR_TC_DEBUG', 'GLAMR_PDL', 'GLAMR_LBS_STAGES', 'GLAMR_TC_NTILE']
-ECHO_ENV = FORBIDDEN_ENV + ['GLAMR_ALLREDUCE', 'OMP_NUM_THREADS', 'NCCL_ALGO', 'NCCL_PROTO']
+ECHO_ENV = FORBIDDEN_ENV + ['GLAMR_ITER_PATH', 'GLAMR_ALLREDUCE', 'OMP_NUM_THREADS', 'NCCL_ALGO', 'NCCL_PROTO']
 ALL_EXTRAS = ['north_star', 'c4', 'c3', 'c5']
 
 
@@ -300,10 +300,17 @@ class StageLoop:
         self.hist = torch.zeros((hist_rows, L.NUM_TERMS + 1), device=ctx.dev)
         lib, lr = model._lib, float(specs['opt_lr'])
 
-        def iteration():
-            model._backward()
-            L.check(lib.glamr_opt_apply(model._opt, L.ptr(model._theta), L.ptr(model._reduce), lr, L.ptr(self.hist), L.NUM_TERMS + 1,
-                                        L.stream_ptr()), 'apply')
+        if ctx.world == 1:
+            # one GPU: the library's own iteration (Adam fused into the tail of the backward pass), launched eagerly here and
+            # captured below into ONE graph per step
+            def iteration():
+                L.check(lib.glamr_opt_iterate(model._opt, L.ptr(model._theta), L.ptr(model._reduce), lr, L.ptr(self.hist), L.NUM_TERMS + 1,
+                                              1, 0, L.stream_ptr()), 'iterate')
+        else:
+            def iteration():
+                model._backward()            # backward pass + NCCL all-reduce of [grad | term sums]
+                L.check(lib.glamr_opt_apply(model._opt, L.ptr(model._theta), L.ptr(model._reduce), lr, L.ptr(self.hist), L.NUM_TERMS + 1,
+                                            L.stream_ptr()), 'apply')
         self.iteration = iteration
         self.native = getattr(model, '_peer_ok', False)
         self.graph = None

@@ -287,6 +287,22 @@ struct AdamState {
   double* beta_pow;   // [0] beta1^t, [1] beta2^t, [2] step count (as a double)
 };
 
+// torch.optim.Adam on theta[lo, hi) with this iteration's bias corrections (same arithmetic as apply_kernel)
+__device__ __forceinline__ void adam_range(const OptCtx& c, float* __restrict__ theta, const float* __restrict__ grad, const AdamState& ad, int lo, int hi,
+                                           float bc2s, float step_size) {
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (!c.pb.active[i]) continue;
+    const float g = grad[i];
+    float m = ad.m[i], v = ad.v[i];
+    m = m + 0.1f * (g - m);
+    v = v * 0.999f + 0.001f * g * g;
+    const float denom = sqrtf(v) / bc2s + 1e-8f;
+    theta[i] = theta[i] - step_size * (m / denom);
+    ad.m[i] = m;
+    ad.v[i] = v;
+  }
+}
+
 __device__ void write_losses(const OptCtx& c, const float* term_sums /*[NUM_TERMS] un-normalised*/, float* loss_terms) {
   double total = 0.0;
   for (int k = 0; k < GLAMR_NUM_TERMS; ++k) {
@@ -344,6 +360,172 @@ __global__ void __launch_bounds__(256) apply_kernel(OptCtx c, float* __restrict_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused tail of the iteration
+// residuals + analytic backward (+ Adam on one GPU) in ONE launch (camera modes 0-2):
+//   phase A  every CTA: one warp per frame-person -- joint assembly, projection, reprojection terms, warp-shuffle sums -> kpg[n]
+//   ticket   per person: the CTA that completes the last frame of person p continues with
+//   phase B  thread per frame: frame_rest (camera-frame pose, cam_traj, smoothness, rel_transform, their gradients), then the
+//            reverse trajectory codec of person p (three reverse scans), regularisers, [Adam on person p's block of theta]
+//   ticket   global: the CTA that finishes the last person runs the camera backward for all frames, folds the fp64 term sums
+//            in fixed slot order, [Adam on the camera block, loss history row, step count].
+// Sums never depend on which CTA happens to be last: every slot is produced by a fixed-order tree and folded in slot order.
+struct FusedArgs {
+  KpGrad* kpg;               // [N] per frame-person joint sums of phase A
+  double* partial;           // [P + 1][NUM_TERMS] slot p: person p, slot P: camera
+  unsigned int* person_ticket;   // [P]
+  unsigned int* global_ticket;   // [1]
+  float* reduce_buf;         // [n_params + NUM_TERMS]
+  float* theta;              // written when do_adam
+  AdamState ad;
+  double lr;
+  float* loss_terms;
+  int hist_stride;
+  int do_adam;
+};
+constexpr int kFusedFramesPerCta = kScanThreads / 32;   // 16 warps -> 16 frame-persons in phase A
+
+__global__ void __launch_bounds__(kScanThreads) residuals_backward_kernel(OptCtx c, SmplDev m, SmplWorkspace wo, int n_ws_begin, FusedArgs a) {
+  __shared__ float sm[kScanThreads / 32 + 1];
+  __shared__ double smd[(kScanThreads / 32) * GLAMR_NUM_TERMS];
+  __shared__ int mine[kFusedFramesPerCta];     // persons this CTA has to finish (a 16-frame window touches <= 2 of them when T >= 16)
+  __shared__ int n_mine;
+  __shared__ bool last_cta;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int P = c.pb.P, T = c.pb.T, N = P * T, J = c.pb.J;
+  // Adam constants of THIS iteration (beta powers are advanced by the very last CTA after everybody has read them)
+  const double b1 = a.ad.beta_pow[0] * 0.9, b2 = a.ad.beta_pow[1] * 0.999, step = a.ad.beta_pow[2];
+  const float bc2s = (float)sqrt(1.0 - b2);
+  const float step_size = (float)(a.lr / (1.0 - b1));
+
+  // ---- phase A
+  const int n0 = blockIdx.x * kFusedFramesPerCta;
+  {
+    const int n = n0 + wid;
+    if (n < N && n >= c.pb.n_begin && n < c.pb.n_end) {
+      const int p = n / T, t = n - p * T;
+      const int nl = n - n_ws_begin;
+      const float* tw = c.sc.trans_world + (size_t)n * 3;
+      const float sc = c.pb.scale_all ? c.pb.scale_all[n] : 1.0f;
+      float root[3], Rc[9], tc[3], Rs[9];
+      raw_joint(m, wo, nl, m.joint_map[0], root);
+      mat34_R(c.sc.cam + (size_t)t * 12, Rc);
+      tc[0] = c.sc.cam[(size_t)t * 12 + 3]; tc[1] = c.sc.cam[(size_t)t * 12 + 7]; tc[2] = c.sc.cam[(size_t)t * 12 + 11];
+      rodrigues_smplx(c.sc.orient_world + (size_t)n * 3, Rs);
+      KpGrad kg;
+      kg.clear();
+      for (int k = lane; k < J; k += 32) {
+        float v[3], jw[3];
+        raw_joint(m, wo, nl, m.joint_map[k], v);
+        jw[0] = (v[0] - root[0]) * sc + tw[0];
+        jw[1] = (v[1] - root[1]) * sc + tw[1];
+        jw[2] = (v[2] - root[2]) * sc + tw[2];
+        float* o = c.sc.joints_world + ((size_t)n * J + k) * 3;
+        o[0] = jw[0]; o[1] = jw[1]; o[2] = jw[2];
+        kp_joint_terms(c, p, t, k, jw, Rc, tc, Rs, tw, kg);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { kg.g_tc[k] = warp_sum(kg.g_tc[k]); kg.g_tw[k] = warp_sum(kg.g_tw[k]); }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { kg.g_Rc[k] = warp_sum(kg.g_Rc[k]); kg.g_Rs[k] = warp_sum(kg.g_Rs[k]); }
+      kg.kp = warp_sum(kg.kp);
+      kg.dist = warp_sum(kg.dist);
+      if (lane == 0) a.kpg[n] = kg;
+    }
+  }
+  // ---- per-person tickets: count the frames of each person this CTA covered
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    int cnt = 0;
+    const int n1 = min(n0 + kFusedFramesPerCta, N);
+    for (int p = n0 / T; p < P && p * T < n1; ++p) {
+      const int lo = max(n0, p * T), hi = min(n1, (p + 1) * T);
+      if (hi <= lo) continue;
+      const unsigned int old = atomicAdd(&a.person_ticket[p], (unsigned int)(hi - lo));
+      if (old + (unsigned int)(hi - lo) == (unsigned int)T) {
+        a.person_ticket[p] = 0u;               // ready for the next iteration (nobody else touches it any more)
+        mine[cnt++] = p;
+      }
+    }
+    n_mine = cnt;
+  }
+  __syncthreads();
+  if (n_mine == 0) return;
+  __threadfence();                              // acquire: kpg of the other CTAs
+
+  for (int q = 0; q < n_mine; ++q) {
+    const int p = mine[q];
+    const glamr_person_t& ps = c.pb.persons[p];
+    const int len = ps.len;
+    const size_t nb = (size_t)p * T + ps.start;
+    TermAcc acc;
+    acc.clear();
+    // ---- phase B1: per-frame residuals of person p
+    for (int t = tid; t < T; t += kScanThreads) {
+      const int n = p * T + t;
+      if (n >= c.pb.n_begin && n < c.pb.n_end) {
+        const KpGrad kg = a.kpg[n];
+        frame_rest(c, p, t, kg, acc);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { c.sc.g_orient[(size_t)n * 3 + k] = 0.0f; c.sc.g_trans[(size_t)n * 3 + k] = 0.0f; }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) c.sc.g_cam[(size_t)n * 12 + k] = 0.0f;
+      }
+    }
+    __syncthreads();
+    // ---- phase B2: reverse trajectory codec
+    for (int t = tid; t < T; t += kScanThreads) traj_back_pre(c, p, t, acc);
+    __syncthreads();
+    block_scan_inplace(c.sc.g_xy + 2 * nb, len, 2, true, sm);
+    block_scan_inplace(c.sc.g_xy + 2 * nb + 1, len, 2, true, sm);
+    __syncthreads();
+    for (int i = tid; i < len; i += kScanThreads) traj_back_mid(c, p, i, acc);
+    __syncthreads();
+    block_scan_inplace(c.sc.g_head + nb, len, 1, true, sm);
+    __syncthreads();
+    for (int i = tid; i < len; i += kScanThreads) traj_back_post(c, p, i, acc);
+    block_reduce_terms(acc, a.partial + (size_t)p * GLAMR_NUM_TERMS, smd);
+    __syncthreads();                            // this CTA's gradient stores are visible to all of its threads
+    if (a.do_adam) {
+      const int lo = ps.off_xy, hi = (p + 1 < P) ? c.pb.persons[p + 1].off_xy : c.pb.n_params;   // person p's contiguous block of theta
+      adam_range(c, a.theta, a.reduce_buf, a.ad, lo, hi, bc2s, step_size);
+    }
+  }
+  // ---- global ticket over the persons
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int old = atomicAdd(a.global_ticket, (unsigned int)n_mine);
+    last_cta = (old + (unsigned int)n_mine == (unsigned int)P);
+    if (last_cta) *a.global_ticket = 0u;
+  }
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence();
+  {
+    TermAcc acc;
+    acc.clear();
+    for (int t = tid; t < T; t += kScanThreads) camera_backward(c, t, acc);
+    block_reduce_terms(acc, a.partial + (size_t)P * GLAMR_NUM_TERMS, smd);
+    __syncthreads();
+    reduce_tail(c, a.partial, P + 1, a.reduce_buf, smd);
+    __syncthreads();
+    if (a.do_adam) {
+      adam_range(c, a.theta, a.reduce_buf, a.ad, 0, c.pb.persons[0].off_xy, bc2s, step_size);     // camera block precedes the persons
+      if (tid == 0) {
+        if (a.loss_terms) write_losses(c, a.reduce_buf + c.pb.n_params, a.loss_terms + (a.hist_stride > 0 ? (size_t)step * a.hist_stride : 0));
+        a.ad.beta_pow[0] = b1;
+        a.ad.beta_pow[1] = b2;
+        a.ad.beta_pow[2] = step + 1.0;
+      }
+    }
+  }
+}
+
 }  // namespace glamr
 
 using namespace glamr;
@@ -356,7 +538,9 @@ struct glamr_opt {
   AdamState adam;
   double* partial;
   int n_slots, slots_res, slots_cam, cam_blocks;   // partial-sum slots: residual CTAs | P + cam_blocks (traj/cam kernel) | slots_cam (mode 3)
-  unsigned int* tickets;                           // [2] last-block-done counters (backward tail, apply)
+  unsigned int* tickets;                           // [0] backward tail, [1] apply, [2] fused global, [4 .. 4+P) fused per person
+  KpGrad* kpg;                                     // [N] phase-A sums of the fused tail kernel
+  int fused;                                       // residuals + backward (+ Adam) in one launch (camera modes 0-2); GLAMR_ITER_PATH=legacy turns it off
   void* arena;
   size_t arena_bytes;
   float gs[GLAMR_NUM_TERMS];
@@ -409,7 +593,8 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   auto take = [&](size_t nfl) { size_t o = floats; floats += (nfl + 63) & ~(size_t)63; return o; };
   const size_t o_partial = take((size_t)st->n_slots * GLAMR_NUM_TERMS * 2);
   const size_t o_beta = take(8);
-  const size_t o_ticket = take(4);
+  const size_t o_ticket = take(8 + (size_t)pb->P);
+  const size_t o_kpg = take(N * (sizeof(KpGrad) / sizeof(float)));
   const size_t o_heading = take(N), o_xy = take(2 * N), o_tl = take(11 * N), o_ob = take(3 * N), o_tb = take(3 * N),
                o_ow = take(3 * N), o_tw = take(3 * N), o_cam = take(12 * T), o_caminv = take(12 * T), o_camd6 = take(6 * T),
                o_jw = take(N * J * 3), o_kp = take(N * J * 2), o_ociw = take(3 * N), o_tciw = take(3 * N), o_go = take(3 * N),
@@ -425,6 +610,11 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   st->partial = (double*)(b + o_partial);
   st->adam.beta_pow = (double*)(b + o_beta);
   st->tickets = (unsigned int*)(b + o_ticket);
+  st->kpg = (KpGrad*)(b + o_kpg);
+  {
+    const char* e = getenv("GLAMR_ITER_PATH");
+    st->fused = !(e && strcmp(e, "legacy") == 0);
+  }
   st->sc.heading = b + o_heading; st->sc.xy = b + o_xy; st->sc.traj_local = b + o_tl; st->sc.orient_base = b + o_ob;
   st->sc.trans_base = b + o_tb; st->sc.orient_world = b + o_ow; st->sc.trans_world = b + o_tw; st->sc.cam = b + o_cam;
   st->sc.cam_inv = b + o_caminv; st->sc.cam_d6 = b + o_camd6; st->sc.joints_world = b + o_jw; st->sc.kp_pred = b + o_kp;
@@ -500,17 +690,21 @@ extern "C" int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* pb,
 
 extern "C" size_t glamr_opt_reduce_count(const glamr_opt_t* st) { return st ? (size_t)st->pb.n_params + GLAMR_NUM_TERMS : 0; }
 
-extern "C" int glamr_opt_launch_count(const glamr_opt_t* st) {
+extern "C" int glamr_opt_launch_count(const glamr_opt_t* st, int via_iterate) {
   if (!st) return GLAMR_EINVAL;
   const bool from_persons = st->pb.cam_mode == GLAMR_CAM_FROM_PERSONS;
   const bool has_frames = st->pb.n_end > st->pb.n_begin;
-  // traj/cam forward [+ cam_forward] + pose_prep + lbs + residuals [+ camera backward + scatter] + traj/cam backward + apply
-  return 1 + (from_persons ? 1 : 0) + (has_frames ? 2 : 0) + 1 + (from_persons ? 2 : 0) + 1 + 1;
+  const int fwd = 1 + (from_persons ? 1 : 0) + (has_frames ? 2 : 0);     // traj/cam forward [+ cam_forward] + pose_prep + lbs
+  if (st->fused && !from_persons)                                        // fused tail; Adam inside it when glamr_opt_iterate runs a single-GPU loop
+    return fwd + 1 + ((via_iterate && st->peer.world <= 1) ? 0 : 1);
+  return fwd + 1 + (from_persons ? 2 : 0) + 1 + 1;                       // residuals [+ camera backward + scatter] + traj/cam backward + apply
 }
 
 #define GLAMR_MARK() do { if (st->timing == 2 && st->n_ev < 24) GLAMR_CUDA_TRY(cudaEventRecord(st->ev[st->n_ev++], s)); } while (0)
 
-static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream, bool use_peers) {
+struct FusedAdam { float* theta; double lr; float* loss_terms; int hist_stride; };
+
+static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream, bool use_peers, const FusedAdam* adam = nullptr) {
   if (!st || !theta || !reduce_buf) return GLAMR_EINVAL;
   PeerCtx pc = st->peer;
   if (!use_peers) pc.world = 0;
@@ -544,6 +738,18 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
     if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
     GLAMR_MARK();
   }
+  if (st->fused && !from_persons && !(use_peers && pc.world > 1)) {
+    FusedArgs a;
+    a.kpg = st->kpg; a.partial = st->partial; a.person_ticket = st->tickets + 4; a.global_ticket = st->tickets + 2;
+    a.reduce_buf = reduce_buf; a.ad = st->adam;
+    a.theta = adam ? adam->theta : nullptr; a.lr = adam ? adam->lr : 0.0; a.loss_terms = adam ? adam->loss_terms : nullptr;
+    a.hist_stride = adam ? adam->hist_stride : 0; a.do_adam = adam ? 1 : 0;
+    GLAMR_CUDA_TRY(launch_pdl(8, residuals_backward_kernel, dim3((N + kFusedFramesPerCta - 1) / kFusedFramesPerCta), dim3(kScanThreads), 0, s, c, st->smpl, wo,
+                              n_begin, a));
+    GLAMR_MARK();
+    return GLAMR_OK;
+  }
+  if (adam) return GLAMR_EINVAL;               // Adam inside the backward pass exists only in the fused kernel
   double* part_res = st->partial;
   double* part_traj = st->partial + (size_t)st->slots_res * GLAMR_NUM_TERMS;
   double* part_cam3 = part_traj + (size_t)(pb.P + st->cam_blocks) * GLAMR_NUM_TERMS;
@@ -647,7 +853,12 @@ extern "C" int glamr_opt_iterate(glamr_opt_t* st, float* theta, float* reduce_bu
   cudaStream_t s = (cudaStream_t)stream;
   int rc, done = 0;
   const bool peers = st->peer.world > 1;      // W > 1: backward publishes, apply sums the peers' slots (no call in between)
+  const bool fused_adam = st->fused && !peers && st->pb.cam_mode != GLAMR_CAM_FROM_PERSONS;
   auto eager = [&](cudaStream_t q) -> int {
+    if (fused_adam) {
+      const FusedAdam fa = {theta, lr, loss_terms, loss_hist_stride};
+      return backward_impl(st, theta, reduce_buf, q, false, &fa);
+    }
     if ((rc = backward_impl(st, theta, reduce_buf, q, peers))) return rc;
     return apply_impl(st, theta, reduce_buf, lr, loss_terms, loss_hist_stride, q, peers);
   };
