@@ -68,12 +68,11 @@ GLAMR_HD void mat34_R(const float* M, float* R) {
 
 // ------------------------------------------------------------------------------------------------ trajectory fwd
 // global_recon_model.py:394-419 + traj_utils.py:65-70: per local frame i of person p.
-GLAMR_HD void traj_pre(const OptCtx& c, int p, int i) {
+// values only: tl[11] = traj_local row of local frame i, returns the (re-wrapped) heading increment that enters the scan
+GLAMR_HD float traj_pre_vals(const OptCtx& c, int p, int i, float* tl) {
   const glamr_person_t& ps = c.pb.persons[p];
-  const int n = p * c.pb.T + ps.start + i;
   const float* pr = ps.traj_local_pred + (size_t)i * 11;
   const float* th = c.theta;
-  float* tl = c.sc.traj_local + (size_t)n * 11;
   float h = safe_atan2(pr[10], pr[9]);
   if (i == 0) {
     h += th[ps.off_heading];
@@ -91,7 +90,14 @@ GLAMR_HD void traj_pre(const OptCtx& c, int p, int i) {
   const float ch = cosf(h), sh = sinf(h);
   tl[9] = ch;
   tl[10] = sh;
-  c.sc.heading[n] = safe_atan2(sh, ch);
+  return safe_atan2(sh, ch);
+}
+GLAMR_HD void traj_pre(const OptCtx& c, int p, int i) {
+  const int n = p * c.pb.T + c.pb.persons[p].start + i;
+  float tl[11];
+  c.sc.heading[n] = traj_pre_vals(c, p, i, tl);
+#pragma unroll
+  for (int k = 0; k < 11; ++k) c.sc.traj_local[(size_t)n * 11 + k] = tl[k];
 }
 // after the inclusive scan of heading: rotate d_xy of frame i >= 1 by heading[i-1]   (traj_utils.py:76-77)
 GLAMR_HD void traj_mid(const OptCtx& c, int p, int i) {
@@ -117,25 +123,24 @@ GLAMR_HD void local_quat(const float* d6, float heading, float* q_hl, float* loc
   aa_to_quat(ha, hq);
   quat_mul(hq, local_q, q_hl);
 }
-GLAMR_HD void traj_post(const OptCtx& c, int p, int t) {
+// world pose of absolute frame t from its traj_local row `tl`, scanned heading and scanned xy (ignored outside the exist range);
+// writes orient/trans base + world of frame-person n, returns nothing else
+GLAMR_HD void traj_post_vals(const OptCtx& c, int p, int t, const float* tl, float heading, float x, float y, float* ow_out) {
   const glamr_person_t& ps = c.pb.persons[p];
   const int T = c.pb.T;
   const int n = p * T + t;
   const int i = t - ps.start;
   float ob[3], tb[3];
   if (i >= 0 && i < ps.len) {
-    const float* tl = c.sc.traj_local + (size_t)n * 11;
     float q_hl[4], lq[4], hq[4], q[4];
-    local_quat(tl + 3, c.sc.heading[n], q_hl, lq, hq);
+    local_quat(tl + 3, heading, q_hl, lq, hq);
     const float base[4] = {0.5f, 0.5f, 0.5f, 0.5f};
     quat_mul(q_hl, base, q);
     quat_to_aa(q, ob);
-    tb[0] = c.sc.xy[2 * (size_t)n]; tb[1] = c.sc.xy[2 * (size_t)n + 1]; tb[2] = tl[2];
+    tb[0] = x; tb[1] = y; tb[2] = tl[2];
   } else {
 #pragma unroll
     for (int k = 0; k < 3; ++k) { ob[k] = ps.orient_base_init[t * 3 + k]; tb[k] = ps.trans_base_init[t * 3 + k]; }
-    float* tl = c.sc.traj_local + (size_t)n * 11;
-    for (int k = 0; k < 11; ++k) tl[k] = 0.0f;
   }
   float ow[3], tw[3];
 #pragma unroll
@@ -163,6 +168,19 @@ GLAMR_HD void traj_post(const OptCtx& c, int p, int t) {
     c.sc.trans_base[(size_t)n * 3 + k] = tb[k];
     c.sc.orient_world[(size_t)n * 3 + k] = ow[k];
     c.sc.trans_world[(size_t)n * 3 + k] = tw[k];
+    if (ow_out) ow_out[k] = ow[k];
+  }
+}
+GLAMR_HD void traj_post(const OptCtx& c, int p, int t) {
+  const glamr_person_t& ps = c.pb.persons[p];
+  const int n = p * c.pb.T + t;
+  const int i = t - ps.start;
+  float* tl = c.sc.traj_local + (size_t)n * 11;
+  if (i >= 0 && i < ps.len) {
+    traj_post_vals(c, p, t, tl, c.sc.heading[n], c.sc.xy[2 * (size_t)n], c.sc.xy[2 * (size_t)n + 1], nullptr);
+  } else {
+    for (int k = 0; k < 11; ++k) tl[k] = 0.0f;
+    traj_post_vals(c, p, t, tl, 0.0f, 0.0f, 0.0f, nullptr);
   }
 }
 

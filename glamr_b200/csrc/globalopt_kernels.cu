@@ -361,6 +361,85 @@ __global__ void __launch_bounds__(256) apply_kernel(OptCtx c, float* __restrict_
 }
 
 
+
+// ------------------------------------------------------------------------------------------------ fused head of the iteration
+// trajectory codec + camera + SMPL pose preparation in ONE launch.  CTA (p, j) owns the 16 frames [16 j, 16 j + 16) of person p:
+// it recomputes the person's heading / xy prefix sums up to its last frame in SHARED memory (O(T) trivial flops per CTA instead
+// of a grid-wide dependency on one scanning CTA), finishes the world pose of its own frames, and then runs the kinematic chain of
+// those frames with one warp per frame (pose_prep_frame).  Camera modes 0-2: the CTAs of person 0 also evaluate the camera of
+// their frames.  Results are bit-identical to traj_cam_forward_kernel + pose_prep_kernel (same scan tree, same formulas).
+constexpr int kFwdFrames = kScanThreads / 32;
+__global__ void __launch_bounds__(kScanThreads) forward_pose_kernel(OptCtx c, SmplDev m, SmplWorkspace wo, int n_ws_begin, int with_cam,
+                                                                    int chunks_per_person, int lpad) {
+  extern __shared__ float fwd_dyn[];
+  __shared__ float sm[kScanThreads / 32 + 1];
+  __shared__ float s_orient[kFwdFrames][3];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = blockIdx.x * kScanThreads + tid; i < c.pb.n_params + GLAMR_NUM_TERMS; i += gridDim.x * kScanThreads) c.sc.grad[i] = 0.0f;
+  const int p = blockIdx.x / chunks_per_person, j = blockIdx.x - p * chunks_per_person;
+  const int T = c.pb.T;
+  const int t0 = j * kFwdFrames, t1 = min(t0 + kFwdFrames, T);
+  const glamr_person_t& ps = c.pb.persons[p];
+  const int len = ps.len, start = ps.start;
+  const int cnt = min(len, t1 - start);               // local frames [0, cnt) feed this chunk's prefix sums (<= 0: chunk precedes the track)
+  float* s_head = fwd_dyn;
+  float* s_x = fwd_dyn + lpad;
+  float* s_y = fwd_dyn + 2 * lpad;
+  for (int i = tid; i < cnt; i += kScanThreads) {
+    float tl[11];
+    s_head[i] = traj_pre_vals(c, p, i, tl);
+    s_x[i] = tl[0];
+    s_y[i] = tl[1];
+  }
+  __syncthreads();
+  if (cnt > 0) block_scan_inplace(s_head, cnt, 1, false, sm);
+  __syncthreads();
+  for (int i = tid; i < cnt; i += kScanThreads) {
+    if (i > 0) {                                       // traj_utils.py:76-77: d_xy of frame i rotated by heading[i-1]
+      const float h = s_head[i - 1];
+      const float ct = cosf(h), st = sinf(h);
+      const float x = s_x[i], y = s_y[i];
+      s_x[i] = x * ct - y * st;
+      s_y[i] = x * st + y * ct;
+    }
+  }
+  __syncthreads();
+  if (cnt > 0) {
+    block_scan_inplace(s_x, cnt, 1, false, sm);
+    block_scan_inplace(s_y, cnt, 1, false, sm);
+  }
+  __syncthreads();
+  if (tid < t1 - t0) {
+    const int t = t0 + tid, i = t - start;
+    const size_t n = (size_t)p * T + t;
+    float tl[11], head = 0.0f, x = 0.0f, y = 0.0f;
+    if (i >= 0 && i < len) {
+      traj_pre_vals(c, p, i, tl);
+      head = s_head[i]; x = s_x[i]; y = s_y[i];
+      c.sc.heading[n] = head;
+      c.sc.xy[2 * n] = x;
+      c.sc.xy[2 * n + 1] = y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 11; ++k) tl[k] = 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 11; ++k) c.sc.traj_local[n * 11 + k] = tl[k];
+    float ow[3];
+    traj_post_vals(c, p, t, tl, head, x, y, ow);
+    s_orient[tid][0] = ow[0]; s_orient[tid][1] = ow[1]; s_orient[tid][2] = ow[2];
+  }
+  if (with_cam && p == 0 && tid >= 32 && tid < 32 + (t1 - t0)) cam_forward(c, t0 + tid - 32);
+  __syncthreads();
+  if (wid < t1 - t0) {
+    const int n = p * T + t0 + wid;
+    if (n >= c.pb.n_begin && n < c.pb.n_end)
+      pose_prep_frame(m, n - n_ws_begin, s_orient[wid], c.pb.smpl_pose_all + (size_t)n * 69, c.pb.smpl_beta_all + (size_t)n * kNB, wo, lane);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ fused tail of the iteration
 // residuals + analytic backward (+ Adam on one GPU) in ONE launch (camera modes 0-2):
 //   phase A  every CTA: one warp per frame-person -- joint assembly, projection, reprojection terms, warp-shuffle sums -> kpg[n]
@@ -540,7 +619,9 @@ struct glamr_opt {
   int n_slots, slots_res, slots_cam, cam_blocks;   // partial-sum slots: residual CTAs | P + cam_blocks (traj/cam kernel) | slots_cam (mode 3)
   unsigned int* tickets;                           // [0] backward tail, [1] apply, [2] fused global, [4 .. 4+P) fused per person
   KpGrad* kpg;                                     // [N] phase-A sums of the fused tail kernel
-  int fused;                                       // residuals + backward (+ Adam) in one launch (camera modes 0-2); GLAMR_ITER_PATH=legacy turns it off
+  int fused;                                       // fused head (trajectory + camera + pose prep) and fused tail (residuals + backward [+ Adam], camera
+                                                   // modes 0-2) kernels; GLAMR_ITER_PATH=legacy selects the one-kernel-per-phase path
+  size_t fwd_smem_set;
   void* arena;
   size_t arena_bytes;
   float gs[GLAMR_NUM_TERMS];
@@ -694,7 +775,7 @@ extern "C" int glamr_opt_launch_count(const glamr_opt_t* st, int via_iterate) {
   if (!st) return GLAMR_EINVAL;
   const bool from_persons = st->pb.cam_mode == GLAMR_CAM_FROM_PERSONS;
   const bool has_frames = st->pb.n_end > st->pb.n_begin;
-  const int fwd = 1 + (from_persons ? 1 : 0) + (has_frames ? 2 : 0);     // traj/cam forward [+ cam_forward] + pose_prep + lbs
+  const int fwd = 1 + (from_persons ? 1 : 0) + (has_frames ? (st->fused ? 1 : 2) : 0);     // forward [+ cam_forward] [+ pose_prep] + lbs
   if (st->fused && !from_persons)                                        // fused tail; Adam inside it when glamr_opt_iterate runs a single-GPU loop
     return fwd + 1 + ((via_iterate && st->peer.world <= 1) ? 0 : 1);
   return fwd + 1 + (from_persons ? 2 : 0) + 1 + 1;                       // residuals [+ camera backward + scatter] + traj/cam backward + apply
@@ -715,23 +796,37 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   const int N = pb.P * pb.T;
   OptCtx c = make_ctx(st, theta, reduce_buf);
   const bool from_persons = pb.cam_mode == GLAMR_CAM_FROM_PERSONS;
-  GLAMR_CUDA_TRY(launch_pdl(1, traj_cam_forward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1));   // also zeroes reduce_buf
-  GLAMR_MARK();
-  if (from_persons) {          // the camera is the mean of the persons' world transforms: needs traj_forward of all persons
-    GLAMR_CUDA_TRY(launch_pdl(1, cam_forward_kernel, dim3(st->slots_cam), dim3(kFrameThreads), 0, s, c));
-  }
-  GLAMR_MARK();
-  // SMPL for the persons this rank owns (global_recon_model.py:517-524); tile-major scratch (A, pf) is local to the launch
+  // SMPL for the frame-persons this rank owns (global_recon_model.py:517-524); tile-major scratch (A, pf) is local to the launch
   const int n_begin = pb.n_begin, n_end = pb.n_end;
   SmplWorkspace wo = st->ws;
   wo.jposed += (size_t)n_begin * kNJ * 3;
   wo.vcompact += (size_t)n_begin * st->smpl.S * 3;
   wo.root_raw += (size_t)n_begin * 3;
+  const int lpad = (pb.T + 31) & ~31;
+  const size_t fwd_smem = (size_t)3 * lpad * sizeof(float);
+  const bool fused_fwd = st->fused && fwd_smem <= 200 * 1024;
+  if (fused_fwd) {
+    if (fwd_smem > 48 * 1024 && st->fwd_smem_set < fwd_smem) {
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(forward_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+      st->fwd_smem_set = fwd_smem;
+    }
+    const int chunks = (pb.T + kFwdFrames - 1) / kFwdFrames;
+    GLAMR_CUDA_TRY(launch_pdl(1, forward_pose_kernel, dim3(pb.P * chunks), dim3(kScanThreads), fwd_smem, s, c, st->smpl, wo, n_begin,
+                              from_persons ? 0 : 1, chunks, lpad));      // also zeroes reduce_buf
+  } else {
+    GLAMR_CUDA_TRY(launch_pdl(1, traj_cam_forward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1));   // also zeroes reduce_buf
+  }
+  GLAMR_MARK();
+  if (from_persons) {          // the camera is the mean of the persons' world transforms: needs traj_forward of all persons
+    GLAMR_CUDA_TRY(launch_pdl(1, cam_forward_kernel, dim3(st->slots_cam), dim3(kFrameThreads), 0, s, c));
+  }
+  GLAMR_MARK();
   if (n_end > n_begin) {
     const int nn = n_end - n_begin;
     int rc;
-    if ((rc = launch_pose_prep(st->smpl, nn, st->sc.orient_world + (size_t)n_begin * 3, pb.smpl_pose_all + (size_t)n_begin * 69,
-                               pb.smpl_beta_all + (size_t)n_begin * kNB, 1, wo, s, true))) return rc;
+    if (!fused_fwd)
+      if ((rc = launch_pose_prep(st->smpl, nn, st->sc.orient_world + (size_t)n_begin * 3, pb.smpl_pose_all + (size_t)n_begin * 69,
+                                 pb.smpl_beta_all + (size_t)n_begin * kNB, 1, wo, s, true))) return rc;
     GLAMR_MARK();
     if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
     if ((rc = launch_lbs(st->smpl, 0, nn, pb.smpl_beta_all + (size_t)n_begin * kNB, wo, nullptr, s, true))) return rc;

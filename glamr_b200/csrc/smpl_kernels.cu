@@ -24,78 +24,9 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(SmplDev m, int n, const 
   pdl_launch_dependents();
   pdl_wait();
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
   if (f >= n) return;
-  const int j = lane < kNJ ? lane : kNJ - 1;
-  float r[3];
-  if (j == 0) {
-    r[0] = orient ? orient[f * 3 + 0] : 0.0f;
-    r[1] = orient ? orient[f * 3 + 1] : 0.0f;
-    r[2] = orient ? orient[f * 3 + 2] : 0.0f;
-  } else {
-    const float* bp = body_pose + (size_t)f * 69 + (j - 1) * 3;
-    r[0] = bp[0]; r[1] = bp[1]; r[2] = bp[2];
-  }
-  float R[9];
-  rodrigues_smplx(r, R);
-  float J[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float v = m.j_template[j * 3 + c];
-    if (use_betas) {
-      const float* js = m.j_shapedirs + (j * 3 + c) * kNB;
-      const float* b = betas + (size_t)f * kNB;
-#pragma unroll
-      for (int l = 0; l < kNB; ++l) v = fmaf(js[l], b[l], v);
-    }
-    J[c] = v;
-  }
-  if (lane >= 1 && lane < kNJ) {
-    // pose feature (R_j - I), stored tile-major [n/32][chunk = j-1][k][n%32] so the LBS kernel fetches a CTA's
-    // [9 x 32] chunk with one bulk copy
-    float* pf = w.pf + (((size_t)(f >> 5) * kNChunks + (lane - 1)) * kChunkK) * 32 + (f & 31);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) pf[k * 32] = R[k] - ((k % 4 == 0) ? 1.0f : 0.0f);
-  }
-
-  float GR[9], Gt[3];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) GR[k] = R[k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) Gt[k] = J[k];
-  const int par = m.parents[j] < 0 ? 0 : m.parents[j];
-  const int lev = m.level[j];
-  for (int l = 1; l < m.n_levels; ++l) {
-    float pR[9], pt[3], pJ[3];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) pR[k] = __shfl_sync(0xffffffffu, GR[k], par);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) pt[k] = __shfl_sync(0xffffffffu, Gt[k], par);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) pJ[k] = __shfl_sync(0xffffffffu, J[k], par);
-    if (lev == l) {
-      float nR[9], rel[3], nt[3];
-      mat3_mul(pR, R, nR);
-      rel[0] = J[0] - pJ[0]; rel[1] = J[1] - pJ[1]; rel[2] = J[2] - pJ[2];
-      mat3_vec(pR, rel, nt);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) GR[k] = nR[k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) Gt[k] = nt[k] + pt[k];
-    }
-  }
-  if (lane < kNJ) {
-    float* jp = w.jposed + ((size_t)f * kNJ + j) * 3;
-    jp[0] = Gt[0]; jp[1] = Gt[1]; jp[2] = Gt[2];
-    float GJ[3];
-    mat3_vec(GR, J, GJ);
-    // A_j (3x4 row-major, 12 floats) stored tile-major: [n/32][j][n%32][12], so the LBS kernel fetches a CTA's
-    // [24][32][12] tile with one bulk copy and a lane (= frame) reads its 12 floats with three LDS.128 (48-byte lane
-    // stride: the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups)
-    float4* A = reinterpret_cast<float4*>(w.A + (((size_t)(f >> 5) * kNJ + j) * 32 + (f & 31)) * 12);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) A[i] = make_float4(GR[i * 3 + 0], GR[i * 3 + 1], GR[i * 3 + 2], Gt[i] - GJ[i]);
-  }
+  pose_prep_frame(m, f, orient ? orient + (size_t)f * 3 : nullptr, body_pose + (size_t)f * 69, use_betas ? betas + (size_t)f * kNB : nullptr, w,
+                  threadIdx.x & 31);
 }
 
 // ------------------------------------------------------------------------------------------------ lbs_kernel
