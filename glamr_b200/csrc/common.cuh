@@ -40,6 +40,18 @@ constexpr int kVPad = kNVTiles * kVTile;     // 6912
 constexpr int kTileCols = kVTile * 3;        // 384 posedirs columns per tile
 constexpr int kChunkK = 9;                   // pose-feature rows per pipeline stage (= one joint's 3x3)
 constexpr int kNChunks = kPF / kChunkK;      // 23
+// tensor-core blend GEMM  v_posed[frame, col] = sum_k feat[frame, k] * basis[col, k]  (smpl_kernels.cu, lbs_blend_tc_kernel):
+// k = 0..206 pose feature x posedirs, 207..216 betas x shapedirs, 217 = 1 x v_template, zero padded to 224
+constexpr int kTcFeat = kPF + kNB + 1;       // 218
+constexpr int kTcK = 224;                    // K padded to a multiple of the per-stage chunk
+constexpr int kTcChunkK = 8;                 // one tcgen05 kind::tf32 MMA step per pipeline stage
+constexpr int kTcChunks = kTcK / kTcChunkK;  // 28
+constexpr int kTcM = 128;                    // frames per CTA tile (= TMEM lanes)
+constexpr int kTcN = 256;                    // basis columns per CTA tile (= TMEM columns)
+constexpr int kTcNTiles = (kV * 3 + kTcN - 1) / kTcN;   // 81
+constexpr int kTcCols = kTcNTiles * kTcN;    // 20736
+constexpr int kTcAStageFloats = 2 * (kTcChunkK / 4) * kTcM * 4;   // hi | lo images of a [128 x 8] K-major core-matrix tile: 2048 floats
+constexpr int kTcBStageFloats = 2 * (kTcChunkK / 4) * kTcN * 4;   // 4096 floats
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +95,35 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 // waits for the previous grid's results (wait) only where it first touches them.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- tcgen05 (UMMA) helpers: shared-memory descriptor of a K-major, un-swizzled operand tile and one kind::tf32 MMA ----
+// rows = rows of the operand tile (128 for X, NT for W): fixes the leading byte offset between 16-byte K groups
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(const void* smem_ptr, int rows) {
+  // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout_type=0 [61,64)
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((rows * 16) >> 4) << 16;     // leading byte offset: next 16-byte K group
+  d |= (uint64_t)(128 >> 4) << 32;             // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// x = hi + lo with hi = tf32(x), lo = tf32(x - hi): the operands of the 3xTF32 tensor-core products (hi*hi + lo*hi + hi*lo)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

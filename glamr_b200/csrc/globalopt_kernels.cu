@@ -775,7 +775,7 @@ extern "C" int glamr_opt_launch_count(const glamr_opt_t* st, int via_iterate) {
   if (!st) return GLAMR_EINVAL;
   const bool from_persons = st->pb.cam_mode == GLAMR_CAM_FROM_PERSONS;
   const bool has_frames = st->pb.n_end > st->pb.n_begin;
-  const int fwd = 1 + (from_persons ? 1 : 0) + (has_frames ? (st->fused ? 1 : 2) : 0);     // forward [+ cam_forward] [+ pose_prep] + lbs
+  const int fwd = 1 + (from_persons ? 1 : 0) + (has_frames ? (st->fused ? 0 : 1) + lbs_kernel_count(st->smpl) : 0);     // forward [+ cam_forward] [+ pose_prep] + lbs
   if (st->fused && !from_persons)                                        // fused tail; Adam inside it when glamr_opt_iterate runs a single-GPU loop
     return fwd + 1 + ((via_iterate && st->peer.world <= 1) ? 0 : 1);
   return fwd + 1 + (from_persons ? 2 : 0) + 1 + 1;                       // residuals [+ camera backward + scatter] + traj/cam backward + apply

@@ -88,31 +88,6 @@ __global__ void __launch_bounds__(256) gemm_bias_act_kernel(int M, int N, int K,
 constexpr int TCM = 128, TCK = 32;                              // N tile (NT) is a template parameter: 128, or 32 for one-tile-high problems
 constexpr int kTcATileFloats = TCM * TCK;                       // 4096 floats = 16 KB (hi or lo of the X tile)
 
-// rows = rows of the operand tile (128 for X, NT for W): fixes the leading byte offset between 16-byte K groups
-__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(const void* smem_ptr, int rows) {
-  // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout_type=0 [61,64)
-  const uint32_t addr = smem_u32(smem_ptr);
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((rows * 16) >> 4) << 16;     // leading byte offset: next 16-byte K group
-  d |= (uint64_t)(128 >> 4) << 32;             // stride byte offset: next 8-row group
-  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-  lo = __uint_as_float(l);
-}
 __device__ __forceinline__ float4 split_tf32_4(const float4 v, float4& lo) {
   float4 hi;
   split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);

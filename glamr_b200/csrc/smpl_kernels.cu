@@ -296,6 +296,224 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ tensor-core LBS
+// The shape blend + pose blend of SMPL is one contraction  v_posed[frame, col] = sum_k feat[frame, k] basis[col, k]
+// (k: 207 pose features x posedirs | 10 betas x shapedirs | 1 x v_template; lbs.py:240,256-267), i.e. a [n x 218] x [218 x 20670]
+// GEMM.  lbs_blend_tc_kernel runs it on the 5th-generation tensor cores with FP32 accuracy (3xTF32: hi*hi + lo*hi + hi*lo,
+// |error| ~ 2e-7 on the blended vertex): both operands are PRE-SPLIT into tf32 hi / lo and pre-tiled in global memory as the UMMA
+// K-major core-matrix image (basis once at glamr_smpl_create, features by pose_prep_frame), so a pipeline stage is two 1-D bulk
+// TMA copies (8 KB of A, 16 KB of B) with no SIMT work on the operand path.  CTA tile = 128 frames (TMEM lanes) x 256 basis columns
+// (TMEM columns), K in 28 steps of 8; warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.commit -> mbarrier),
+// warps 2-5 = epilogue: tcgen05.ld the accumulator and store it TRANSPOSED ([column][frame]) so that lbs_skin_kernel (lanes =
+// frames) reads 128 contiguous bytes per vertex coordinate.  4 stages x 24 KB = 96 KB of shared memory and 256 TMEM columns per
+// CTA: two CTAs per SM overlap one's epilogue with the other's main loop.
+constexpr int kTcStages = 4;
+constexpr int kTcThreads = 192;
+constexpr uint32_t kTcABytes = kTcAStageFloats * sizeof(float);      // 8,192
+constexpr uint32_t kTcBBytes = kTcBStageFloats * sizeof(float);      // 16,384
+constexpr size_t kTcSmemBytes = (size_t)kTcStages * (kTcABytes + kTcBBytes) + 128;
+
+__global__ void __launch_bounds__(kTcThreads) lbs_blend_tc_kernel(SmplDev m, SmplWorkspace w) {
+  extern __shared__ __align__(128) unsigned char tc_raw[];
+  float* As = reinterpret_cast<float*>(tc_raw);                                   // [stages][hi | lo][2][128][4]
+  float* Bs = As + kTcStages * kTcAStageFloats;                                   // [stages][hi | lo][2][256][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(Bs + kTcStages * kTcBStageFloats); // [stages]
+  uint64_t* empty = full + kTcStages;                                             // [stages]
+  uint64_t* acc_full = empty + kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntile = blockIdx.x, mtile = blockIdx.y;
+  pdl_launch_dependents();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const float* gA = w.tcA + (size_t)mtile * kTcChunks * kTcAStageFloats;
+      const float* gB = m.tcB + (size_t)ntile * kTcChunks * kTcBStageFloats;
+      // the basis is a model constant: its first stages are requested before this grid waits for the kernel that writes the features
+      for (int c = 0; c < kTcStages; ++c) {
+        mbar_expect_tx_only(&full[c], kTcBBytes);
+        tma_bulk_g2s(Bs + c * kTcBStageFloats, gB + (size_t)c * kTcBStageFloats, kTcBBytes, &full[c]);
+      }
+      pdl_wait();
+      for (int c = 0; c < kTcChunks; ++c) {
+        const int s = c % kTcStages;
+        if (c >= kTcStages) {
+          mbar_wait(&empty[s], ((c / kTcStages) - 1) & 1);                       // the MMAs that read this stage have completed
+          mbar_expect_tx(&full[s], kTcABytes + kTcBBytes);
+          tma_bulk_g2s(Bs + s * kTcBStageFloats, gB + (size_t)c * kTcBStageFloats, kTcBBytes, &full[s]);
+        } else {
+          mbar_expect_tx(&full[s], kTcABytes);
+        }
+        tma_bulk_g2s(As + s * kTcAStageFloats, gA + (size_t)c * kTcAStageFloats, kTcABytes, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+      for (int c = 0; c < kTcChunks; ++c) {
+        const int s = c % kTcStages;
+        mbar_wait(&full[s], (c / kTcStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float* a = As + s * kTcAStageFloats;
+        const float* b = Bs + s * kTcBStageFloats;
+        const uint64_t dah = umma_desc_kmajor_noswizzle(a, kTcM), dal = umma_desc_kmajor_noswizzle(a + kTcAStageFloats / 2, kTcM);
+        const uint64_t dbh = umma_desc_kmajor_noswizzle(b, kTcN), dbl = umma_desc_kmajor_noswizzle(b + kTcBStageFloats / 2, kTcN);
+        umma_tf32(tmem_d, dah, dbh, idesc, c > 0 ? 1u : 0u);
+        umma_tf32(tmem_d, dal, dbh, idesc, 1u);
+        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+        // arrives on empty[s] once every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(acc_full)) : "memory");
+    }
+  } else {
+    // ---- epilogue: warp q = warp % 4 may read TMEM lanes 32 q .. 32 q + 31 (= frames of this tile)
+    mbar_wait(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int frame = mtile * kTcM + q * 32 + lane;                              // < w.mpad by construction
+    float* out = w.vpT + (size_t)ntile * kTcN * w.mpad + frame;
+#pragma unroll 1
+    for (int cc = 0; cc < kTcN / 32; ++cc) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, "
+          "%28, %29, %30, %31}, [%32];\n"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+            "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) out[(size_t)(cc * 32 + j) * w.mpad] = __uint_as_float(v[j]);   // 32 lanes = 32 consecutive frames: 128 B per column
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTcN));
+}
+
+// Skinning of the blended vertices (lbs.py:273-284): CTA = 128 vertices x 32 frames, warp = 32 vertices, lane = frame.
+// The tile's relative joint transforms [24][32][12] arrive by one bulk TMA copy; joint indices / weights are warp-uniform
+// (prefetched one vertex per lane, broadcast by shuffles); v_posed comes from the transposed blend output with one coalesced
+// 128-byte load per vertex coordinate; a lane reads its frame's A_j with three conflict-free LDS.128.
+constexpr size_t kSkinSmemBytes = (size_t)kATileFloats * sizeof(float) + 16;
+template <int KREG>
+__global__ void __launch_bounds__(kLbsThreads) lbs_skin_kernel(SmplDev m, int n_begin, int n_end, SmplWorkspace w, float* __restrict__ vertices) {
+  extern __shared__ __align__(128) unsigned char skin_raw[];
+  float* As = reinterpret_cast<float*>(skin_raw);
+  uint64_t* abar = reinterpret_cast<uint64_t*>(As + kATileFloats);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int vtile = blockIdx.x;
+  const int f0 = n_begin + blockIdx.y * kFramesPerCta;
+  pdl_launch_dependents();
+  if (tid == 0) {
+    mbar_init(abar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int vbase = (tid >> 5) * 32;
+  const int gvl = min(vtile * kVTile + vbase + lane, kVPad - 1);
+  float4 my_w = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned int my_j = 0;
+  if (KREG > 0) {
+    my_w = *reinterpret_cast<const float4*>(m.skin_w + (size_t)gvl * 4);
+    my_j = *reinterpret_cast<const unsigned int*>(m.skin_j + (size_t)gvl * 4);
+  }
+  const int my_ci = m.compact_of_vertex[gvl];
+  pdl_wait();                                   // A (pose_prep) and vpT (blend GEMM) are written by preceding kernels
+  if (tid == 0) {
+    mbar_expect_tx(abar, (uint32_t)kATileFloats * sizeof(float));
+    tma_bulk_g2s(As, w.A + (size_t)(f0 >> 5) * kATileFloats, (uint32_t)kATileFloats * sizeof(float), abar);
+  }
+  const int fr = lane;
+  const int n = f0 + fr;
+  const bool n_ok = n < n_end;
+  const float* vp = w.vpT + (size_t)(vtile * kVTile + vbase) * 3 * w.mpad + n;      // n < mpad (frames padded to 128)
+  mbar_wait(abar, 0);
+  constexpr int U = 4;
+#pragma unroll 1
+  for (int i0 = 0; i0 < 32; i0 += U) {
+    float x[U], y[U], z[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int gv = vtile * kVTile + vbase + i0 + u;
+      const bool ok = gv < kV;
+      const float* q = vp + (size_t)(i0 + u) * 3 * w.mpad;
+      x[u] = ok ? q[0] : 0.0f;
+      y[u] = ok ? q[w.mpad] : 0.0f;
+      z[u] = ok ? q[2 * (size_t)w.mpad] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u;
+      const int gv = vtile * kVTile + vbase + i;
+      if (gv >= kV) break;
+      const int ci = __shfl_sync(0xffffffffu, my_ci, i);
+      float T[12];
+      if (KREG > 0) {
+        const float w0 = __shfl_sync(0xffffffffu, my_w.x, i), w1 = __shfl_sync(0xffffffffu, my_w.y, i);
+        const float w2 = __shfl_sync(0xffffffffu, my_w.z, i), w3 = __shfl_sync(0xffffffffu, my_w.w, i);
+        const unsigned int jj = __shfl_sync(0xffffffffu, my_j, i);
+        const float4* a0 = reinterpret_cast<const float4*>(As + ((jj & 0xff) * 32 + fr) * 12);
+        const float4* a1 = reinterpret_cast<const float4*>(As + (((jj >> 8) & 0xff) * 32 + fr) * 12);
+        const float4* a2 = reinterpret_cast<const float4*>(As + (((jj >> 16) & 0xff) * 32 + fr) * 12);
+        const float4* a3 = reinterpret_cast<const float4*>(As + (((jj >> 24) & 0xff) * 32 + fr) * 12);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float4 q0 = a0[r], q1 = a1[r], q2 = a2[r], q3 = a3[r];
+          T[4 * r + 0] = fmaf(w3, q3.x, fmaf(w2, q2.x, fmaf(w1, q1.x, w0 * q0.x)));
+          T[4 * r + 1] = fmaf(w3, q3.y, fmaf(w2, q2.y, fmaf(w1, q1.y, w0 * q0.y)));
+          T[4 * r + 2] = fmaf(w3, q3.z, fmaf(w2, q2.z, fmaf(w1, q1.z, w0 * q0.z)));
+          T[4 * r + 3] = fmaf(w3, q3.w, fmaf(w2, q2.w, fmaf(w1, q1.w, w0 * q0.w)));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = 0.0f;
+        for (int sidx = 0; sidx < m.K; ++sidx) {
+          const int jj = m.skin_j[(size_t)gv * m.K + sidx];
+          const float wt = m.skin_w[(size_t)gv * m.K + sidx];
+          const float* a = As + (jj * 32 + fr) * 12;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) T[k] = fmaf(wt, a[k], T[k]);
+        }
+      }
+      const float ox = fmaf(T[0], x[u], fmaf(T[1], y[u], fmaf(T[2], z[u], T[3])));
+      const float oy = fmaf(T[4], x[u], fmaf(T[5], y[u], fmaf(T[6], z[u], T[7])));
+      const float oz = fmaf(T[8], x[u], fmaf(T[9], y[u], fmaf(T[10], z[u], T[11])));
+      if (n_ok) {
+        if (vertices) {
+          float* o = vertices + ((size_t)n * kV + gv) * 3;
+          o[0] = ox; o[1] = oy; o[2] = oz;
+        }
+        if (ci >= 0) {
+          float* o = w.vcompact + ((size_t)n * m.S + ci) * 3;
+          o[0] = ox; o[1] = oy; o[2] = oz;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ joints_finalize
 // One warp per frame-person: gather the mapped joints from [24 LBS | picks | extra regressed], re-root at joint 0
 // and apply scale / root translation   (lib/models/smpl.py:299-315)
@@ -367,11 +585,44 @@ int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* 
 
 // pdl: launch with the programmatic-serialization attribute.  Only for callers whose betas are long-lived constants
 // (the optimiser): the kernel reads betas / shapedirs / posedirs BEFORE it waits for the preceding grid.
+static int g_lbs_path = -1;
+int lbs_path() {
+  if (g_lbs_path < 0) {
+    const char* e = getenv("GLAMR_LBS_PATH");
+    g_lbs_path = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return g_lbs_path;
+}
+int lbs_kernel_count(const SmplDev& m) { return (lbs_path() == 1 && m.tcB) ? 2 : 1; }
+
 int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices, cudaStream_t s,
                bool pdl) {
   if (n_end <= n_begin) return GLAMR_OK;
   if (n_begin % kFramesPerCta != 0) return GLAMR_EINVAL;   // the tile-major scratch is indexed by whole frame tiles
   dim3 grid(kNVTiles, (n_end - n_begin + kFramesPerCta - 1) / kFramesPerCta);
+  static bool attrs = false;
+  const int path = lbs_path();             // 1: tensor-core blend GEMM + skinning kernel (default), 0: the one-kernel FP32 SIMT path
+  if (!attrs) {
+    attrs = true;
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
+  }
+  if (path == 1 && m.tcB && w.tcA && n_begin == 0) {
+    const int mtiles = (n_end + kTcM - 1) / kTcM;
+    if (pdl) {
+      GLAMR_CUDA_TRY(launch_pdl(4, lbs_blend_tc_kernel, dim3(kTcNTiles, mtiles), dim3(kTcThreads), kTcSmemBytes, s, m, w));
+      if (m.K == 4) GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_kernel<4>, grid, dim3(kLbsThreads), kSkinSmemBytes, s, m, n_begin, n_end, w, vertices));
+      else GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_kernel<0>, grid, dim3(kLbsThreads), kSkinSmemBytes, s, m, n_begin, n_end, w, vertices));
+    } else {
+      lbs_blend_tc_kernel<<<dim3(kTcNTiles, mtiles), kTcThreads, kTcSmemBytes, s>>>(m, w);
+      GLAMR_LAUNCH_CHECK();
+      if (m.K == 4) lbs_skin_kernel<4><<<grid, kLbsThreads, kSkinSmemBytes, s>>>(m, n_begin, n_end, w, vertices);
+      else lbs_skin_kernel<0><<<grid, kLbsThreads, kSkinSmemBytes, s>>>(m, n_begin, n_end, w, vertices);
+      GLAMR_LAUNCH_CHECK();
+    }
+    return GLAMR_OK;
+  }
   static int stages = 0, dbg = 0;
   if (!stages) {
     const char* e = getenv("GLAMR_LBS_STAGES");
@@ -475,6 +726,32 @@ extern "C" int glamr_smpl_create(glamr_smpl_t** out, const float* v_template, co
       }
     if ((rc = upload(h, t, &d.pd_tiles))) goto fail;
   }
+  {  // blend basis [20736 cols][224 k] = posedirs^T | shapedirs | v_template, tf32 hi / lo, UMMA K-major core-matrix image per
+     // (256-column tile, 8-wide K chunk): [hi | lo][k group (4 wide)][256 cols][4]
+    auto tf32_rna = [](float x) {            // cvt.rna.tf32.f32: round to nearest, ties away from zero, 10-bit mantissa
+      uint32_t u;
+      memcpy(&u, &x, 4);
+      u = (u + 0x1000u) & 0xFFFFE000u;
+      float r;
+      memcpy(&r, &u, 4);
+      return r;
+    };
+    std::vector<float> img((size_t)kTcNTiles * kTcChunks * kTcBStageFloats, 0.0f);
+    for (int col = 0; col < kV * 3; ++col) {
+      const int tile = col / kTcN, r = col % kTcN;
+      for (int k = 0; k < kTcFeat; ++k) {
+        float v;
+        if (k < kPF) v = posedirs[(size_t)k * kV * 3 + col];
+        else if (k < kPF + kNB) v = shapedirs[(size_t)col * kNB + (k - kPF)];      // shapedirs [v][c][l] = [col][l]
+        else v = v_template[col];
+        const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+        float* q = &img[((size_t)tile * kTcChunks + (k >> 3)) * kTcBStageFloats + ((((k >> 2) & 1) * kTcN + r) * 4) + (k & 3)];
+        q[0] = hi;
+        q[kTcBStageFloats / 2] = lo;
+      }
+    }
+    if ((rc = upload(h, img, &d.tcB))) goto fail;
+  }
   {
     std::vector<float> vt((size_t)kVPad * 3, 0.0f), sd((size_t)kVPad * 30, 0.0f);
     memcpy(vt.data(), v_template, (size_t)kV * 3 * sizeof(float));
@@ -560,6 +837,12 @@ extern "C" int glamr_smpl_destroy(glamr_smpl_t* m) {
   return GLAMR_OK;
 }
 
+extern "C" int glamr_smpl_set_lbs_path(int path) {
+  if (path != 0 && path != 1) return GLAMR_EINVAL;
+  g_lbs_path = path;
+  return GLAMR_OK;
+}
+
 extern "C" int glamr_smpl_info(const glamr_smpl_t* m, int what) {
   if (!m) return GLAMR_EINVAL;
   switch (what) {
@@ -599,7 +882,8 @@ extern "C" int glamr_smpl_fk24(const glamr_smpl_t* m, int n, const float* global
   if (workspace_bytes < glamr_smpl_workspace_bytes(m, n)) return GLAMR_ENOSPACE;
   if (n == 0) return GLAMR_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const SmplWorkspace w = smpl_carve_workspace(workspace, n, m->dev.S);
+  SmplWorkspace w = smpl_carve_workspace(workspace, n, m->dev.S);
+  w.tcA = nullptr;                             // FK only: no blend features
   int rc = launch_pose_prep(m->dev, n, global_orient, body_pose, nullptr, 0, w, s);
   if (rc) return rc;
   fk24_finalize_kernel<<<(n * kNJ * 3 + 255) / 256, 256, 0, s>>>(n, w.jposed, root_trans, root_scale, joints);

@@ -9,6 +9,9 @@ struct SmplDev {
   // dense constants
   const float* pd_tiles;     // [54][207][384]  posedirs, vertex-tile major: one contiguous 13,824 B block per
                              //                 (tile, 9-row chunk) so a CTA streams its slab with 1-D bulk TMA
+  const float* tcB;          // [81 col tiles][28 K chunks][hi | lo][2 K groups][256 cols][4]  the blend basis (posedirs | shapedirs |
+                             //                 v_template) pre-split into tf32 hi / lo and pre-tiled as the UMMA K-major core-matrix image:
+                             //                 one contiguous 16 KB block per (tile, chunk) = one bulk copy per pipeline stage
   const float* v_template;   // [6912][3]  (padded with zeros)
   const float* shapedirs;    // [6912][30] ([v][c][l] as in the model file)
   const float* j_template;   // [24][3]    J_regressor @ v_template
@@ -37,11 +40,18 @@ struct SmplWorkspace {
   float* jposed;    // [n][24][3]   posed LBS joints
   float* vcompact;  // [n][S][3]    skinned support vertices
   float* root_raw;  // [n][3]       un-rooted joint 0 (for vertex re-rooting)
+  float* tcA;       // [n/128][28][hi | lo][2][128][4]  blend features (pose feature | betas | 1 | 0-pad), tf32 hi / lo, UMMA image per
+                    //              (128-frame tile, K chunk): 8 KB contiguous = one bulk copy per stage
+  float* vpT;       // [20736][mpad]  blended vertices v_posed, TRANSPOSED (column-major over frames) so that the skinning kernel's
+                    //              lanes = frames read 128 contiguous bytes per vertex coordinate
+  int mpad;         // frames padded to a multiple of 128
 };
 
 inline size_t smpl_workspace_floats(int n, int S) {
   const size_t n32 = ((size_t)n + 31) / 32 * 32;   // the pose feature is tile-major over whole 32-frame tiles
-  return (size_t)n * (kNJ * 3 + (size_t)S * 3 + 3) + n32 * (kPFPad + kNJ * 12) + 64;
+  const size_t n128 = ((size_t)n + kTcM - 1) / kTcM * kTcM;
+  return (size_t)n * (kNJ * 3 + (size_t)S * 3 + 3) + n32 * (kPFPad + kNJ * 12) + 64 + 64 +
+         (n128 / kTcM) * kTcChunks * kTcAStageFloats + (size_t)kTcCols * n128;
 }
 inline SmplWorkspace smpl_carve_workspace(void* base, int n, int S) {
   SmplWorkspace w;
@@ -50,7 +60,11 @@ inline SmplWorkspace smpl_carve_workspace(void* base, int n, int S) {
   w.pf = p; p += ((size_t)n + 31) / 32 * 32 * kPFPad;
   w.jposed = p; p += (size_t)n * kNJ * 3;
   w.vcompact = p; p += (size_t)n * S * 3;
-  w.root_raw = p;
+  w.root_raw = p; p += (size_t)n * 3;
+  p = (float*)(((uintptr_t)p + 255) & ~(uintptr_t)255);          // bulk-copy sources: 16-byte aligned (256 for good measure)
+  w.mpad = (int)(((size_t)n + kTcM - 1) / kTcM * kTcM);
+  w.tcA = p; p += (size_t)(w.mpad / kTcM) * kTcChunks * kTcAStageFloats;
+  w.vpT = p;
   return w;
 }
 
@@ -112,6 +126,29 @@ __device__ __forceinline__ void pose_prep_frame(const SmplDev& m, int f, const f
 #pragma unroll
     for (int k = 0; k < 9; ++k) pf[k * 32] = R[k] - ((k % 4 == 0) ? 1.0f : 0.0f);
   }
+  if (w.tcA) {
+    // the same features (+ betas, + the constant 1 that multiplies v_template, + zero padding) as the A operand of the
+    // tensor-core blend GEMM: tf32 hi / lo, K-major core-matrix image of this frame's 128-frame tile
+    float* tile = w.tcA + (size_t)(f >> 7) * kTcChunks * kTcAStageFloats;
+    const int r = f & 127;
+    auto put = [&](int k, float v) {
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      float* q = tile + (size_t)(k >> 3) * kTcAStageFloats + (((k >> 2) & 1) * kTcM + r) * 4 + (k & 3);
+      q[0] = hi;
+      q[kTcAStageFloats / 2] = lo;
+    };
+    if (lane >= 1 && lane < kNJ) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) put((lane - 1) * 9 + k, R[k] - ((k % 4 == 0) ? 1.0f : 0.0f));
+    } else if (lane == 0) {
+#pragma unroll
+      for (int l = 0; l < kNB; ++l) put(kPF + l, beta ? beta[l] : 0.0f);
+      put(kPF + kNB, 1.0f);
+#pragma unroll
+      for (int k = kTcFeat; k < kTcK; ++k) put(k, 0.0f);
+    }
+  }
 
   float GR[9], Gt[3];
 #pragma unroll
@@ -161,6 +198,8 @@ int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* 
 // n_begin..n_end: frame-person range to skin.  vertices may be NULL.
 int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices,
                cudaStream_t s, bool pdl = false);
+int lbs_path();                              // 1 tensor-core blend + skinning kernels, 0 one-kernel FP32 SIMT path
+int lbs_kernel_count(const SmplDev& m);      // kernels one launch_lbs call launches
 int launch_joints_finalize(const SmplDev& m, int n, int orig_joints, const float* root_trans, const float* root_scale,
                            const SmplWorkspace& w, float* joints, cudaStream_t s);
 int launch_reroot_vertices(int n, const float* root_raw, const float* root_trans, const float* root_scale,

@@ -66,7 +66,17 @@ def test_rowop_vjps_match_autograd():
 
 
 # ------------------------------------------------------------------------------------------------ SMPL
-def test_smpl_forward_matches_reference_golden(smpl_assets):
+@pytest.fixture(params=['tensor_core', 'simt'])
+def lbs_path(request):
+    """both implementations of the blend + skinning: the default tcgen05 3xTF32 blend GEMM + skinning kernel, and the single
+    FP32 SIMT kernel"""
+    from glamr_b200 import lib as L
+    L.check(L.load().glamr_smpl_set_lbs_path(1 if request.param == 'tensor_core' else 0), 'set_lbs_path')
+    yield request.param
+    L.check(L.load().glamr_smpl_set_lbs_path(1), 'set_lbs_path')
+
+
+def test_smpl_forward_matches_reference_golden(smpl_assets, lbs_path):
     from glamr_b200.smpl import SMPL
     g = load_golden('smpl')
     smpl = SMPL(smpl_assets, pose_type='body26fk', device=DEV)
@@ -91,7 +101,7 @@ def test_smpl_forward_matches_reference_golden(smpl_assets):
 
 
 @pytest.mark.parametrize('n', [1, 31, 32, 33, 300, 1000])
-def test_smpl_forward_matches_oracle_ragged_sizes(n, smpl_assets):
+def test_smpl_forward_matches_oracle_ragged_sizes(n, smpl_assets, lbs_path):
     """frame counts around the 32-frame CTA tile, all 6890 vertices compared"""
     from glamr_b200.smpl import SMPL
     from oracle.smpl import OracleSMPL
@@ -111,7 +121,27 @@ def test_smpl_forward_matches_oracle_ragged_sizes(n, smpl_assets):
         assert (out.vertices[-8:].cpu() - v).abs().max() < 2e-5
 
 
-def test_smpl_dense_skinning_model(smpl_assets):
+def test_smpl_tensor_core_and_simt_paths_agree(smpl_assets):
+    """all 6890 vertices of 300 frame-persons: 3xTF32 tensor-core blend vs the FP32 FMA kernel"""
+    from glamr_b200 import lib as L
+    from glamr_b200.smpl import SMPL
+    smpl = SMPL(smpl_assets, pose_type='body26fk', device=DEV)
+    gen = torch.Generator().manual_seed(11)
+    n = 300
+    o, p = torch.randn(n, 3, generator=gen).to(DEV), (torch.randn(n, 69, generator=gen) * 0.4).to(DEV)
+    b, t = torch.randn(n, 10, generator=gen).to(DEV), torch.randn(n, 3, generator=gen).to(DEV)
+    outs = []
+    for path in (1, 0):
+        L.check(L.load().glamr_smpl_set_lbs_path(path), 'set_lbs_path')
+        r = smpl(global_orient=o, body_pose=p, betas=b, root_trans=t)
+        outs.append((r.joints.clone(), r.vertices.clone()))
+    L.check(L.load().glamr_smpl_set_lbs_path(1), 'set_lbs_path')
+    dj, dv = (outs[0][0] - outs[1][0]).abs().max().item(), (outs[0][1] - outs[1][1]).abs().max().item()
+    print(f'tensor-core vs SIMT: joints {dj:.2e}, vertices {dv:.2e}')
+    assert dj < 5e-6 and dv < 5e-6
+
+
+def test_smpl_dense_skinning_model(smpl_assets, lbs_path):
     """a model whose skinning weights are dense (24 per vertex) takes the generic-K kernel"""
     from glamr_b200.smpl import SMPL
     from oracle.smpl import OracleSMPL

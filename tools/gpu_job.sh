@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+echo "=== 1 legacy+simt"; GLAMR_ITER_PATH=legacy GLAMR_LBS_PATH=simt timeout 900 python -m pytest tests -m gpu -q -k "not tensor_core and not paths_agree" > gpurun_out/t1_legacy_simt.log 2>&1; tail -15 gpurun_out/t1_legacy_simt.log
+echo "=== 2 fused+simt"; GLAMR_LBS_PATH=simt timeout 600 python -m pytest tests -m gpu -q -k "globalopt or residual or graph or optimize or pipeline" > gpurun_out/t2_fused_simt.log 2>&1; tail -15 gpurun_out/t2_fused_simt.log
+echo "=== 3 default"; timeout 900 python -m pytest tests -m gpu -q > gpurun_out/t3_default.log 2>&1; tail -25 gpurun_out/t3_default.log
+echo "=== 4 bench"; BENCH_DEBUG=1 timeout 900 python bench.py > gpurun_out/bench_r02a.json 2> gpurun_out/bench_r02a.err; tail -3 gpurun_out/bench_r02a.err; head -c 300 gpurun_out/bench_r02a.json; echo
+echo "=== 5 bench legacy"; GLAMR_ITER_PATH=legacy GLAMR_LBS_PATH=simt timeout 300 python bench.py --extras none --no-cpu-baseline > gpurun_out/bench_r02a_legacy.json 2>/dev/null; head -c 300 gpurun_out/bench_r02a_legacy.json; echo
+echo "=== 6 bench fused+simt"; GLAMR_LBS_PATH=simt timeout 300 python bench.py --extras none --no-cpu-baseline > gpurun_out/bench_r02a_fused_simt.json 2>/dev/null; head -c 300 gpurun_out/bench_r02a_fused_simt.json; echo
