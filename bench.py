@@ -300,9 +300,10 @@ class StageLoop:
         self.hist = torch.zeros((hist_rows, L.NUM_TERMS + 1), device=ctx.dev)
         lib, lr = model._lib, float(specs['opt_lr'])
 
-        if ctx.world == 1:
-            # one GPU: the library's own iteration (Adam fused into the tail of the backward pass), launched eagerly here and
-            # captured below into ONE graph per step
+        self.native = bool(getattr(model, '_peer_ok', False))      # gradient all-reduce over NVLink peer memory inside the Adam kernel
+        if ctx.world == 1 or self.native:
+            # the library's own iteration (one GPU: Adam fused into the tail of the backward pass; peer path: the all-reduce fused
+            # into the Adam kernel), launched eagerly here and captured below into ONE graph per step
             def iteration():
                 L.check(lib.glamr_opt_iterate(model._opt, L.ptr(model._theta), L.ptr(model._reduce), lr, L.ptr(self.hist), L.NUM_TERMS + 1,
                                               1, 0, L.stream_ptr()), 'iterate')
@@ -312,26 +313,17 @@ class StageLoop:
                 L.check(lib.glamr_opt_apply(model._opt, L.ptr(model._theta), L.ptr(model._reduce), lr, L.ptr(self.hist), L.NUM_TERMS + 1,
                                             L.stream_ptr()), 'apply')
         self.iteration = iteration
-        self.native = getattr(model, '_peer_ok', False)
         self.graph = None
-        if self.native:          # opt-in peer-memory reduction: the library owns the captured iteration
-            def step():
-                L.check(lib.glamr_opt_iterate(model._opt, L.ptr(model._theta), L.ptr(model._reduce), lr, L.ptr(self.hist),
-                                              L.NUM_TERMS + 1, 1, 1, L.stream_ptr()), 'iterate')
-            for _ in range(warmup):
-                step()
-            self.step = step
-        else:
-            for _ in range(warmup):
+        for _ in range(warmup):
+            iteration()
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
                 iteration()
-            try:
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    iteration()
-            except Exception:
-                self.graph = None
-                torch.cuda.synchronize()
-            self.step = self.graph.replay if self.graph is not None else iteration
+        except Exception:
+            self.graph = None
+            torch.cuda.synchronize()
+        self.step = self.graph.replay if self.graph is not None else iteration
         for _ in range(3):
             self.step()
 
@@ -458,7 +450,7 @@ def staged_workload(ctx, cfg_id, persons, frames, K, with_e2e=True, cpu_iters=0)
         loop = StageLoop(ctx, model, data, stage, specs, 4 * K + 64, warmup=5)
         cold, warm = loop.time(K)
         res['stages'][stage] = {'ms_per_iter': cold, 'ms_per_iter_l2_warm': warm, 'value': units / (cold * 1e-3), 'iters_per_sec': 1e3 / cold,
-                                'yaml_iterations': specs['opt_niters'], 'cuda_graph': bool(loop.native or loop.graph is not None)}
+                                'yaml_iterations': specs['opt_niters'], 'cuda_graph': bool(loop.graph is not None)}
         if stage == last:
             res['lbs_kernel_ms'] = loop.lbs_ms(20)
             res['lbs_frame_persons_per_launch'] = model._n_range[1] - model._n_range[0]
@@ -555,7 +547,7 @@ def run_ours(args):
     lbs_ms = loop.lbs_ms(min(K, 50))
     n_local = model._n_range[1] - model._n_range[0]
     peer = bool(getattr(model, '_peer_ok', False))
-    graph_on = bool(loop.native or loop.graph is not None)
+    graph_on = bool(loop.graph is not None)
     launches_per_iter = model.launches_per_iteration()
     loop.release()
     del model, loop

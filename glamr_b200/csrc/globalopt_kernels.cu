@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kFrameThreads) camera_scatter_kernel(OptCtx c)
 // element of [grad | term sums] with the epoch into one 8-byte word {value, e} and PUSHES it into slot e & 1, source row
 // `rank`, of every rank's buffer (plain 8-byte stores over NVLink: value and tag arrive together); apply_kernel polls its
 // OWN memory until the word of each source carries tag e and sums the W values in rank order -- the same bits on every
-// rank.  Two slots suffice: a rank can be at most one iteration ahead of the slowest reader (its next apply needs that
+// rank.  (Both halves live in apply_kernel: every thread pushes the elements it owns, then polls for them.)  Two slots suffice: a rank can be at most one iteration ahead of the slowest reader (its next apply needs that
 // reader's next push), so epoch e only ever overwrites epoch e - 2, which every rank has finished reading.
 struct PeerCtx {
   int rank, world;
@@ -185,18 +185,6 @@ __device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long lo
 }
 __device__ __forceinline__ size_t peer_row(const PeerCtx& pc, uint32_t e, int src) {
   return kPeerHeaderWords / 2 + ((size_t)(e & 1u) * GLAMR_MAX_PEERS + src) * pc.slot_elems;
-}
-// last CTA of the backward pass: reduce_buf is final (all other CTAs fenced before their ticket)
-__device__ void peer_publish(const PeerCtx& pc, const float* reduce_buf, int count) {
-  uint32_t* hdr = reinterpret_cast<uint32_t*>(pc.bufs[pc.rank]);
-  const uint32_t e = hdr[0] + 1u;
-  const size_t row = peer_row(pc, e, pc.rank);
-  for (int i = threadIdx.x; i < count; i += blockDim.x) {
-    const unsigned long long w = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(reduce_buf[i]);
-    for (int r = 0; r < pc.world; ++r) st_peer_u64(pc.bufs[r] + row + i, w);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) hdr[0] = e;
 }
 // value of element i published by rank `src` for epoch e (spins on local memory until it has landed)
 __device__ __forceinline__ float peer_take(const PeerCtx& pc, uint32_t e, int src, int i) {
@@ -274,10 +262,6 @@ __global__ void __launch_bounds__(kScanThreads) traj_cam_backward_kernel(OptCtx 
   block_reduce_terms(acc, partial_traj + (size_t)blockIdx.x * GLAMR_NUM_TERMS, smd);
   if (grid_last_block(ticket)) {
     reduce_tail(c, partial_all, n_slots, reduce_buf, smd);
-    if (pc.world > 1) {
-      __syncthreads();
-      peer_publish(pc, reduce_buf, c.pb.n_params + GLAMR_NUM_TERMS);
-    }
   }
 }
 
@@ -328,6 +312,18 @@ __global__ void __launch_bounds__(256) apply_kernel(OptCtx c, float* __restrict_
   pdl_wait();
   const double b1 = ad.beta_pow[0] * 0.9, b2 = ad.beta_pow[1] * 0.999, step = ad.beta_pow[2];
   const uint32_t epoch = pc.world > 1 ? reinterpret_cast<const uint32_t*>(pc.bufs[pc.rank])[1] + 1u : 0u;
+  if (pc.world > 1) {
+    // one-shot all-reduce over NVLink, part 1: every thread PUSHES its own elements of this rank's [grad | term sums], tagged
+    // with the iteration number in the same 8-byte word, into slot (epoch & 1), source row `rank`, of every rank's buffer.  All
+    // pushes of a rank are issued before any of its threads starts polling, so ranks never wait on each other circularly.
+    const size_t row = peer_row(pc, epoch, pc.rank);
+    const int count = c.pb.n_params + GLAMR_NUM_TERMS;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+      const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(reduce_buf[i]);
+      for (int r = 0; r < pc.world; ++r) st_peer_u64(pc.bufs[r] + row + i, w);
+    }
+  }
+  // part 2: a thread polls its OWN memory until the word of each source carries this iteration's tag and sums in rank order
   auto grad_at = [&](int i) -> float {
     if (pc.world <= 1) return reduce_buf[i];
     float g = 0.0f;
@@ -833,7 +829,7 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
     if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
     GLAMR_MARK();
   }
-  if (st->fused && !from_persons && !(use_peers && pc.world > 1)) {
+  if (st->fused && !from_persons) {
     FusedArgs a;
     a.kpg = st->kpg; a.partial = st->partial; a.person_ticket = st->tickets + 4; a.global_ticket = st->tickets + 2;
     a.reduce_buf = reduce_buf; a.ad = st->adam;
