@@ -64,6 +64,44 @@ def make_smpl_assets(seed=0, skin_nnz=4, reg_nnz=8):
     return a
 
 
+def make_h36m_regressor(seed=0, nnz=6):
+    """[17, 6890] joint regressor with the sparsity of the real J_regressor_h36m.npy (4-9 non-zeros per row, rows sum to 1)"""
+    rng = np.random.default_rng(seed + 4242)
+    r = np.zeros((17, NUM_VERTS), np.float32)
+    for i in range(17):
+        vs = rng.choice(NUM_VERTS, nnz, replace=False)
+        r[i, vs] = rng.dirichlet(np.ones(nnz)).astype(np.float32)
+    return r
+
+
+def make_eval_case(num_persons=2, num_fr=60, seed=0, gaps=True):
+    """A (result, ground truth) pair shaped like what Evaluator.compute_sequence_metrics receives (evaluator.py:218-327):
+    `person_data[p]` with the optimiser's output keys, `gt[p]` with AMASS/3DPW-style `pose [T,72]`, `shape [10]`,
+    `root_trans [T,3]`.  The estimate is the ground truth plus smooth errors; person 0 exists on a sub-range."""
+    rng = np.random.default_rng(seed + 99)
+    data = {'person_data': {}, 'gt': {}, 'gt_meta': {}, 'seq_len': num_fr, 'seq_name': 'eval_case'}
+    for p in range(num_persons):
+        T = num_fr
+        pose = rng.normal(0.0, 0.2, (1, 72)) + np.cumsum(rng.normal(0.0, 0.01, (T, 72)), axis=0)
+        pose[:, :3] = np.array([1.2, 1.2, 1.2]) + np.cumsum(rng.normal(0.0, 0.01, (T, 3)), axis=0)
+        shape = rng.normal(0.0, 0.5, 10)
+        trans = np.array([0.8 * p, 0.3, 0.9]) + np.cumsum(rng.normal(0.0, 0.01, (T, 3)), axis=0)
+        vis = make_exist_with_gaps(T, seed=seed * 7 + p, n_gaps=2, min_len=4, max_len=10) if gaps else np.ones(T)
+        exist = np.ones(T, dtype=bool)
+        if p == 0 and T > 20:
+            exist[:3] = False
+            vis[:3] = 0
+        est_pose = pose + rng.normal(0.0, 0.02, pose.shape) + np.cumsum(rng.normal(0.0, 0.002, pose.shape), axis=0)
+        data['gt'][p] = {'pose': pose.astype(np.float32), 'shape': shape.astype(np.float32), 'root_trans': trans.astype(np.float32)}
+        data['person_data'][p] = {
+            'smpl_orient_world': est_pose[:, :3].astype(np.float32), 'smpl_pose': est_pose[:, 3:].astype(np.float32),
+            'smpl_beta': np.repeat((shape + rng.normal(0, 0.1, 10))[None], T, axis=0).astype(np.float32),
+            'root_trans_world': (trans + rng.normal(0.0, 0.01, trans.shape) + np.array([0.05, -0.02, 0.01])).astype(np.float32),
+            'scale': None, 'visible_orig': vis.astype(np.float64), 'exist_frames': exist,
+        }
+    return data
+
+
 def _rodrigues_np(aa):
     return Rotation.from_rotvec(aa.reshape(-1, 3)).as_matrix().reshape(aa.shape[:-1] + (3, 3))
 

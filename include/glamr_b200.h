@@ -282,6 +282,19 @@ int glamr_peer_free(void* dev_ptr);       /* a pointer from glamr_peer_alloc */
 size_t glamr_opt_peer_bytes(const glamr_opt_t* st);
 int glamr_opt_set_peers(glamr_opt_t* st, int rank, int world, void* const* bufs /* [world], own buffer included */);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Evaluation  --  stands behind global_recon/utils/evaluator.py:202-327 (Evaluator.prepare_seq).
+ * glamr_sparse_regress: out[n,rows,3] = R @ vertices[n,V,3] for a regressor given in CSR form (row_ptr [rows+1], col_idx /
+ *   weights [nnz], all DEVICE pointers) -- `torch.matmul(self.J_regressor, smpl_motion.vertices)` (:263,:306); the H36M
+ *   regressor holds ~6 non-zeros per row.
+ * glamr_procrustes_align: per frame, the similarity transform (scale, R, t) that maps S1 [n,J,3] closest to S2 [n,J,3],
+ *   applied to S1 -> out [n,J,3]  (lib/utils/torch_transform.py:282-345 batch_compute_similarity_transform_torch; 3x3 SVD
+ *   by one-sided Jacobi in fp64, reflection fixed through sign(det(U V^T))).
+ * ---------------------------------------------------------------------------------------------------------- */
+int glamr_sparse_regress(int n, int V, int rows, const int32_t* row_ptr, const int32_t* col_idx, const float* weights,
+                         const float* vertices, float* out, void* stream);
+int glamr_procrustes_align(int n, int J, const float* S1, const float* S2, float* out, void* stream);
+
 /* device pointer + element count of an internal output buffer (valid until the handle is destroyed) */
 int glamr_opt_read(glamr_opt_t* st, int what, const float** ptr, size_t* count);
 

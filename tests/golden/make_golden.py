@@ -320,7 +320,33 @@ def camera_term_vectors():
     return rec
 
 
+def evaluator_vectors():
+    """Evaluator.compute_sequence_metrics of the reference (global_recon/utils/evaluator.py) on seeded (estimate, ground truth)
+    pairs.  The reference imports `lib.utils.logging`, a module its tree does not contain (the file is lib/utils/log_utils.py):
+    aliased in sys.modules, like the other import shims; its code is untouched."""
+    import lib.utils.log_utils as LU
+    sys.modules['lib.utils.logging'] = LU
+    from glamr_b200.synthetic import make_eval_case, make_h36m_regressor
+    np.save(os.path.join(ref_env.WORK, 'data', 'J_regressor_h36m.npy'), make_h36m_regressor(0))
+    from global_recon.utils.evaluator import Evaluator
+    out = {}
+    for tag, dataset, P, T, freq in [('p2_t60', '3DPW', 2, 60, 250), ('p1_t300_h36m', 'h36m', 1, 300, 250), ('p1_t90_realign', '3DPW', 1, 90, 40)]:
+        ev = Evaluator('glamr', dataset, device=torch.device('cpu'), log_file='nofile', align_freq=freq, compute_sample=True)
+        data = make_eval_case(P, T, seed=len(out))
+        out[f'{tag}/seed'] = np.array(len(out))
+        md = ev.compute_sequence_metrics(copy.deepcopy(data), 'case', accumulate=False)
+        for k, v in md['metrics'].items():
+            if isinstance(v.avg, np.ndarray):
+                out[f'{tag}/metric/{k}'] = v.avg
+            else:
+                out[f'{tag}/metric/{k}'] = np.array([v.avg, v.count], np.float64)
+    return out
+
+
 def main(only=None):
+    if only == 'evaluator':
+        np.savez_compressed(os.path.join(HERE, 'evaluator.npz'), **evaluator_vectors())
+        return
     if only == 'camera_terms':
         np.savez_compressed(os.path.join(HERE, 'camera_terms.npz'), **camera_term_vectors())
         return

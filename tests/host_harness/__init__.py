@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, 'libglamr_hostmath.so')
 SRC = [os.path.join(HERE, 'harness.cpp'), os.path.join(HERE, 'emu.cpp')]
-DEPS = SRC + [os.path.join(HERE, '..', '..', 'glamr_b200', 'csrc', f) for f in ['glamr_math.cuh', 'rowops.cuh', 'globalopt_frames.cuh']] + \
+DEPS = SRC + [os.path.join(HERE, '..', '..', 'glamr_b200', 'csrc', f) for f in ['glamr_math.cuh', 'rowops.cuh', 'globalopt_frames.cuh', 'eval_math.cuh']] + \
     [os.path.join(HERE, '..', '..', 'include', 'glamr_b200.h')]
 
 

@@ -2,6 +2,7 @@
 // (forward values and hand-derived VJPs) can be checked against torch autograd on the GPU-less build box.
 // The product never loads this library; its compute path is the CUDA library and fails loudly without it.
 #include "../../glamr_b200/csrc/rowops.cuh"
+#include "../../glamr_b200/csrc/eval_math.cuh"
 
 extern "C" {
 
@@ -25,6 +26,11 @@ int glamr_host_rowop_vjp(int op, int n, const float* in0, const float* in1, cons
   for (int i = 0; i < n; ++i)
     glamr::rowop_vjp(op, in0 + (long)i * d0, in1 ? in1 + (long)i * d1 : nullptr, gout + (long)i * dout,
                      gin0 ? gin0 + (long)i * d0 : nullptr, gin1 ? gin1 + (long)i * d1 : nullptr);
+  return 0;
+}
+
+int glamr_host_procrustes(int n, int J, const float* S1, const float* S2, float* out) {
+  for (int f = 0; f < n; ++f) glamr::procrustes_frame(J, S1 + (long)f * J * 3, S2 + (long)f * J * 3, out + (long)f * J * 3);
   return 0;
 }
 }
