@@ -858,6 +858,11 @@ extern "C" size_t glamr_smpl_workspace_bytes(const glamr_smpl_t* m, int n) {
   return smpl_workspace_floats(n, m->dev.S) * sizeof(float);
 }
 
+extern "C" size_t glamr_smpl_fk_workspace_bytes(const glamr_smpl_t* m, int n) {
+  if (!m || n < 0) return 0;
+  return smpl_workspace_floats_fk(n, m->dev.S) * sizeof(float);
+}
+
 extern "C" int glamr_smpl_forward(const glamr_smpl_t* m, int n, const float* global_orient, const float* body_pose,
                                   const float* betas, const float* root_trans, const float* root_scale, int orig_joints,
                                   float* joints, float* vertices, void* workspace, size_t workspace_bytes, void* stream) {
@@ -879,7 +884,7 @@ extern "C" int glamr_smpl_fk24(const glamr_smpl_t* m, int n, const float* global
                                const float* root_trans, const float* root_scale, float* joints, void* workspace,
                                size_t workspace_bytes, void* stream) {
   if (!m || n < 0 || !body_pose || !joints || !workspace) return GLAMR_EINVAL;
-  if (workspace_bytes < glamr_smpl_workspace_bytes(m, n)) return GLAMR_ENOSPACE;
+  if (workspace_bytes < glamr_smpl_fk_workspace_bytes(m, n)) return GLAMR_ENOSPACE;
   if (n == 0) return GLAMR_OK;
   cudaStream_t s = (cudaStream_t)stream;
   SmplWorkspace w = smpl_carve_workspace(workspace, n, m->dev.S);

@@ -47,6 +47,11 @@ struct SmplWorkspace {
   int mpad;         // frames padded to a multiple of 128
 };
 
+// FK only (glamr_smpl_fk24): the kinematic-chain scratch without the blend operands (they are carved last)
+inline size_t smpl_workspace_floats_fk(int n, int S) {
+  const size_t n32 = ((size_t)n + 31) / 32 * 32;
+  return (size_t)n * (kNJ * 3 + (size_t)S * 3 + 3) + n32 * (kPFPad + kNJ * 12) + 64 + 64;
+}
 inline size_t smpl_workspace_floats(int n, int S) {
   const size_t n32 = ((size_t)n + 31) / 32 * 32;   // the pose feature is tile-major over whole 32-frame tiles
   const size_t n128 = ((size_t)n + kTcM - 1) / kTcM * kTcM;

@@ -97,6 +97,7 @@ def load():
                          'glamr_b200 has no CPU fallback.')
     lib = ctypes.CDLL(SO_PATH)
     lib.glamr_smpl_workspace_bytes.restype = ctypes.c_size_t
+    lib.glamr_smpl_fk_workspace_bytes.restype = ctypes.c_size_t
     lib.glamr_sizeof_person.restype = ctypes.c_size_t
     lib.glamr_sizeof_problem.restype = ctypes.c_size_t
     lib.glamr_opt_reduce_count.restype = ctypes.c_size_t

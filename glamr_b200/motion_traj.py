@@ -35,6 +35,46 @@ def _declare(lib):
     lib._nets_declared = True
 
 
+class _GraphCache:
+    """Replays a fixed launch sequence as ONE CUDA graph.  The prior networks are launch-latency bound (about 70 small kernels
+    per 50-frame window, 10 windows for a 300-frame track): `run(key, fn, inputs)` copies `inputs` into static device
+    buffers, replays the graph captured for `key` (same shapes -> same launches) and returns clones of the static outputs.
+    The first call for a key runs `fn` eagerly (lazy initialisation must happen outside capture) and then captures it; if
+    capture is refused the key stays on the eager path."""
+
+    def __init__(self, enabled=True, max_entries=8):
+        self.enabled, self.max_entries, self.entries = enabled, max_entries, {}
+
+    def run(self, key, fn, inputs):
+        if not self.enabled:
+            return fn(*inputs)
+        ent = self.entries.get(key)
+        if ent is None:
+            if len(self.entries) >= self.max_entries:
+                self.entries.pop(next(iter(self.entries)))
+            static_in = [None if x is None else x.clone() for x in inputs]
+            out = fn(*static_in)                                   # eager warm-up; also the result of this first call
+            ent = {'in': static_in, 'graph': None, 'out': None}
+            self.entries[key] = ent
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ent['out'] = fn(*static_in)
+                ent['graph'] = g
+            except Exception:
+                ent['graph'], ent['out'] = None, None
+                torch.cuda.synchronize()
+            return out
+        if ent['graph'] is None:
+            return fn(*inputs)
+        for dst, src in zip(ent['in'], inputs):
+            if dst is not None:
+                dst.copy_(src)
+        ent['graph'].replay()
+        return tuple(o.clone() for o in ent['out']) if isinstance(ent['out'], tuple) else ent['out'].clone()
+
+
 class _Net:
     """opaque glamr_net_t with the parameters of one network"""
 
@@ -54,6 +94,8 @@ class _Net:
 
     def workspace(self, floats):
         if self._ws is None or self._ws.numel() < floats:
+            if self._ws is not None:                 # captured graphs may hold the old address: retire, do not free
+                self._retired = getattr(self, '_retired', []) + [self._ws]
             self._ws = torch.empty(int(floats), dtype=torch.float32, device=self.device)
         return self._ws
 
@@ -72,6 +114,7 @@ class MotionInfillerVAE:
         self.net = _Net(state, device)
         self.device = self.net.device
         self.nz, self.past_nframe, self.cur_nframe, self.fut_nframe = NZ, PAST, CUR, FUT
+        self.graphs = _GraphCache()
 
     def get_latent(self, seq_len):
         return torch.randn((int(np.ceil((seq_len - PAST) / CUR)), NZ))
@@ -80,10 +123,27 @@ class MotionInfillerVAE:
         if recon or not multi_step:
             raise NotImplementedError('only the multi-step sampling path (recon=False) is implemented on CUDA')
         dev = self.device
-        pose_in = batch['in_body_pose'].to(dev, torch.float32)
+        pose_in = batch['in_body_pose'].to(dev, torch.float32).contiguous()
+        frame_mask = batch['frame_mask'].to(dev, torch.float32).contiguous()
+        latent = batch.get('in_motion_latent')
+        latent = None if latent is None else latent.to(dev, torch.float32).contiguous()
+        B0, T = pose_in.shape[:2]
+        self.net.workspace(self.net.lib.glamr_infiller_workspace_floats(B0 * sample_num))        # sized before any capture
+        key = ('infill', B0, T, sample_num, None if latent is None else tuple(latent.shape))
+        with torch.cuda.device(dev):
+            body = self.graphs.run(key, lambda a, b, c: self._windows(a, b, c, sample_num), (pose_in, frame_mask, latent))
+        data = dict(batch)
+        data['infer_out_body_pose'] = body
+        data['infer_out_pose'] = torch.cat([torch.zeros_like(body[..., :3]), body], dim=-1)
+        data['batch_size'], data['seq_len'] = B0, T
+        return data
+
+    def _windows(self, pose_in, frame_mask, latent, sample_num):
+        """motion_infiller_vae.py:618-632: autoregressive 50-frame windows (device tensors in, [B0, S, T, 69] out; no host sync)"""
+        dev = self.device
         B0, T = pose_in.shape[:2]
         pose = pose_in.repeat_interleave(sample_num, dim=0).transpose(0, 1).contiguous().clone()       # [T,B,69]
-        key_pad_all = ~(batch['frame_mask'].to(dev) == 1)
+        key_pad_all = ~(frame_mask == 1)
         key_pad_all = key_pad_all.repeat_interleave(sample_num, dim=0)
         B = B0 * sample_num
         lib = self.net.lib
@@ -91,34 +151,27 @@ class MotionInfillerVAE:
         out = torch.empty((PAST + CUR, B, 69), dtype=torch.float32, device=dev)
         pieces = []
         nwin = int(np.ceil((T - PAST) / CUR))
-        latent = batch.get('in_motion_latent')
-        with torch.cuda.device(dev):
-            for i in range(nwin):
-                s, e = i * CUR, i * CUR + WINDOW
-                eb = min(e, T)
-                win = torch.zeros((WINDOW, B, 69), dtype=torch.float32, device=dev)
-                win[:eb - s] = pose[s:eb]
-                kp = torch.ones((B, WINDOW), dtype=torch.uint8, device=dev)
-                kp[:, :eb - s] = key_pad_all[:, s:eb].to(torch.uint8)
-                kp[:, :PAST] = 0
-                if latent is not None and latent.dim() == 3:                 # [B, windows, nz]: one latent per sequence
-                    eps, rows = latent[:, i].to(dev, torch.float32).repeat_interleave(sample_num, dim=0).contiguous(), B
-                elif latent is not None:
-                    eps, rows = latent[[i]].to(dev, torch.float32).contiguous(), 1
-                else:
-                    eps, rows = torch.randn((B, NZ), device=dev), B
-                L.check(lib.glamr_infiller_window_forward(self.net.h, B, win.data_ptr(), kp.data_ptr(), eps.data_ptr(), rows, out.data_ptr(),
-                                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
-                        'glamr_infiller_window_forward')
-                nfr = min(e - FUT, T) - s
-                pose[s:s + nfr] = out[:nfr]
-                pieces.append(out[:nfr].clone() if i == 0 else out[PAST:nfr].clone())
-        body = torch.cat(pieces, dim=0).transpose(0, 1).reshape(B0, sample_num, T, 69).contiguous()
-        data = dict(batch)
-        data['infer_out_body_pose'] = body
-        data['infer_out_pose'] = torch.cat([torch.zeros_like(body[..., :3]), body], dim=-1)
-        data['batch_size'], data['seq_len'] = B0, T
-        return data
+        for i in range(nwin):
+            s, e = i * CUR, i * CUR + WINDOW
+            eb = min(e, T)
+            win = torch.zeros((WINDOW, B, 69), dtype=torch.float32, device=dev)
+            win[:eb - s] = pose[s:eb]
+            kp = torch.ones((B, WINDOW), dtype=torch.uint8, device=dev)
+            kp[:, :eb - s] = key_pad_all[:, s:eb].to(torch.uint8)
+            kp[:, :PAST] = 0
+            if latent is not None and latent.dim() == 3:                 # [B, windows, nz]: one latent per sequence
+                eps, rows = latent[:, i].repeat_interleave(sample_num, dim=0).contiguous(), B
+            elif latent is not None:
+                eps, rows = latent[[i]].contiguous(), 1
+            else:
+                eps, rows = torch.randn((B, NZ), device=dev), B
+            L.check(lib.glamr_infiller_window_forward(self.net.h, B, win.data_ptr(), kp.data_ptr(), eps.data_ptr(), rows, out.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+                    'glamr_infiller_window_forward')
+            nfr = min(e - FUT, T) - s
+            pose[s:s + nfr] = out[:nfr]
+            pieces.append(out[:nfr].clone() if i == 0 else out[PAST:nfr].clone())
+        return torch.cat(pieces, dim=0).transpose(0, 1).reshape(B0, sample_num, T, 69).contiguous()
 
 
 class TrajPredVAE:
@@ -129,6 +182,7 @@ class TrajPredVAE:
     def __init__(self, state, device, smpl):
         self.net = _Net(state, device)
         self.device, self.smpl, self.nz = self.net.device, smpl, NZ
+        self.graphs = _GraphCache()
 
     def get_latent(self, seq_len):
         return torch.zeros((1, NZ))
@@ -144,7 +198,25 @@ class TrajPredVAE:
         if recon or recon_only or multi_step or sample_num != 1:
             raise NotImplementedError('only single-pass sampling (multi_step_trajpred=false, sample_num=1) is implemented on CUDA')
         dev = self.device
-        body = batch['in_body_pose'].to(dev, torch.float32)                       # [B,T,69]
+        body = batch['in_body_pose'].to(dev, torch.float32).contiguous()           # [B,T,69]
+        B, T = body.shape[:2]
+        dv = lambda k: batch[k].to(dev, torch.float32).contiguous() if k in batch and batch[k] is not None else None
+        latent, ixy, ih = dv('in_traj_latent'), dv('init_xy'), dv('init_heading')
+        self.net.workspace(self.net.lib.glamr_trajpred_workspace_floats(T, B))
+        self.smpl._workspace(B * T, fk_only=True)
+        key = ('traj', B, T, None if latent is None else tuple(latent.shape), ixy is not None, ih is not None)
+        with torch.cuda.device(dev):
+            local, trans, orient = self.graphs.run(key, self._forward, (body, latent, ixy, ih))
+        out = {'infer_out_local_traj_tp': local.view(T, B, 1, 11), 'infer_out_trans_tp': trans.view(T, B, 1, 3),
+               'infer_out_orient_tp': orient.view(T, B, 1, 3)}
+        out['infer_out_orient'] = out['infer_out_orient_tp'].permute(1, 2, 0, 3).contiguous()
+        out['infer_out_trans'] = out['infer_out_trans_tp'].permute(1, 2, 0, 3).contiguous()
+        out['infer_out_pose'] = torch.cat([out['infer_out_orient'], body.unsqueeze(1)], dim=-1)
+        return out
+
+    def _forward(self, body, latent, ixy, ih):
+        """joint-position features (SMPL FK) + the network, device tensors only"""
+        dev = self.device
         B, T = body.shape[:2]
         jp = self.get_joint_pos(body).transpose(0, 1).contiguous()                # [T,B,69]
         lib = self.net.lib
@@ -152,24 +224,14 @@ class TrajPredVAE:
         local = torch.empty((T, B, 11), dtype=torch.float32, device=dev)
         trans = torch.empty((T, B, 3), dtype=torch.float32, device=dev)
         orient = torch.empty((T, B, 3), dtype=torch.float32, device=dev)
-        latent = batch.get('in_traj_latent')
         if latent is not None:
-            eps = latent.to(dev, torch.float32).contiguous()
-            rows = 1 if eps.shape[0] == 1 else B
+            eps, rows = latent, (1 if latent.shape[0] == 1 else B)
         else:
             eps, rows = torch.randn((B, NZ), device=dev), B
-        ixy = batch['init_xy'].to(dev, torch.float32).contiguous() if 'init_xy' in batch else None
-        ih = batch['init_heading'].to(dev, torch.float32).contiguous() if 'init_heading' in batch else None
-        with torch.cuda.device(dev):
-            L.check(lib.glamr_trajpred_forward(self.net.h, T, B, jp.data_ptr(), eps.data_ptr(), rows, None if ixy is None else ixy.data_ptr(),
-                                               None if ih is None else ih.data_ptr(), local.data_ptr(), trans.data_ptr(), orient.data_ptr(),
-                                               ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), 'glamr_trajpred_forward')
-        out = {'infer_out_local_traj_tp': local.view(T, B, 1, 11), 'infer_out_trans_tp': trans.view(T, B, 1, 3),
-               'infer_out_orient_tp': orient.view(T, B, 1, 3)}
-        out['infer_out_orient'] = out['infer_out_orient_tp'].permute(1, 2, 0, 3).contiguous()
-        out['infer_out_trans'] = out['infer_out_trans_tp'].permute(1, 2, 0, 3).contiguous()
-        out['infer_out_pose'] = torch.cat([out['infer_out_orient'], body.unsqueeze(1)], dim=-1)
-        return out
+        L.check(lib.glamr_trajpred_forward(self.net.h, T, B, jp.data_ptr(), eps.data_ptr(), rows, None if ixy is None else ixy.data_ptr(),
+                                           None if ih is None else ih.data_ptr(), local.data_ptr(), trans.data_ptr(), orient.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), 'glamr_trajpred_forward')
+        return local, trans, orient
 
 
 def load_lightning_state_dict(path):

@@ -100,9 +100,13 @@ class SMPL:
             raise L.GlamrError('an SMPL handle is bound to the device it was created on')
         return self
 
-    def _workspace(self, n):
-        need = self._lib.glamr_smpl_workspace_bytes(self._h, n)
+    def _workspace(self, n, fk_only=False):
+        """scratch for n frame-persons.  A buffer that is outgrown is RETIRED, not freed: captured CUDA graphs (the prior
+        networks replay their launch sequence) may still hold its address."""
+        need = (self._lib.glamr_smpl_fk_workspace_bytes if fk_only else self._lib.glamr_smpl_workspace_bytes)(self._h, n)
         if self._ws is None or self._ws.numel() < need:
+            if self._ws is not None:
+                self._ws_retired = getattr(self, '_ws_retired', []) + [self._ws]
             self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
         return self._ws
 
@@ -141,7 +145,7 @@ class SMPL:
         bp, go = self._prep(body_pose, n, 69), self._prep(global_orient, n, 3)
         rt, rs = self._prep(root_trans, n, 3), self._prep(root_scale, n, 0)
         joints = torch.empty((n, 24, 3), dtype=torch.float32, device=self.device)
-        ws = self._workspace(n)
+        ws = self._workspace(n, fk_only=True)
         with torch.cuda.device(self.device):
             L.check(self._lib.glamr_smpl_fk24(self._h, n, L.ptr(go), L.ptr(bp), L.ptr(rt), L.ptr(rs), L.ptr(joints), L.ptr(ws),
                                               ctypes.c_size_t(ws.numel()), L.stream_ptr()), 'glamr_smpl_fk24')

@@ -58,7 +58,8 @@ int glamr_smpl_create(glamr_smpl_t** out, const float* v_template, const float* 
 int glamr_smpl_destroy(glamr_smpl_t* m);
 /* introspection: 0 max skin weights per vertex, 1 support size (vertices feeding picks/regressors), 2 n_map */
 int glamr_smpl_info(const glamr_smpl_t* m, int what);
-size_t glamr_smpl_workspace_bytes(const glamr_smpl_t* m, int n);
+size_t glamr_smpl_workspace_bytes(const glamr_smpl_t* m, int n);       /* glamr_smpl_forward */
+size_t glamr_smpl_fk_workspace_bytes(const glamr_smpl_t* m, int n);    /* glamr_smpl_fk24 (no blend operands) */
 /* Which kernels evaluate the blend + skinning of SMPL.forward: 1 (default) = tcgen05 3xTF32 blend GEMM + skinning kernel,
  * 0 = the single FP32 SIMT kernel (kept for A/B verification; env GLAMR_LBS_PATH=simt selects it at start-up).  Process-wide. */
 int glamr_smpl_set_lbs_path(int path);

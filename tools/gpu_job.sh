@@ -5,3 +5,10 @@ echo "=== 3 default"; timeout 900 python -m pytest tests -m gpu -q > gpurun_out/
 echo "=== 4 bench"; BENCH_DEBUG=1 timeout 900 python bench.py > gpurun_out/bench_r02a.json 2> gpurun_out/bench_r02a.err; tail -3 gpurun_out/bench_r02a.err; head -c 300 gpurun_out/bench_r02a.json; echo
 echo "=== 5 bench legacy"; GLAMR_ITER_PATH=legacy GLAMR_LBS_PATH=simt timeout 300 python bench.py --extras none --no-cpu-baseline > gpurun_out/bench_r02a_legacy.json 2>/dev/null; head -c 300 gpurun_out/bench_r02a_legacy.json; echo
 echo "=== 6 bench fused+simt"; GLAMR_LBS_PATH=simt timeout 300 python bench.py --extras none --no-cpu-baseline > gpurun_out/bench_r02a_fused_simt.json 2>/dev/null; head -c 300 gpurun_out/bench_r02a_fused_simt.json; echo
+echo "=== 7 breakdowns"
+timeout 120 python tools/iter_breakdown.py 2>&1 | tail -1
+GLAMR_LBS_PATH=simt timeout 120 python tools/iter_breakdown.py 2>&1 | tail -1
+GLAMR_ITER_PATH=legacy GLAMR_LBS_PATH=simt timeout 120 python tools/iter_breakdown.py 2>&1 | tail -1
+P=4 CFG=glamr_static_multi timeout 120 python tools/iter_breakdown.py 2>&1 | tail -1
+timeout 200 python tools/e2e_breakdown.py 200 300 > gpurun_out/e2e_breakdown_r02a.txt 2>&1; grep "wall ms" gpurun_out/e2e_breakdown_r02a.txt
+echo "=== 8 ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_r02a.csv python bench.py --steps 3 --warmup 3 --extras none --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | head -c 300; echo
