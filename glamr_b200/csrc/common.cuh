@@ -27,6 +27,11 @@
 #define GLAMR_DBG(x) 0
 #endif
 
+// Which implementation runs when the environment does not say otherwise.  A path becomes the default only after its parity
+// tests passed on a B200 (GLAMR_ITER_PATH=fused|legacy, GLAMR_LBS_PATH=tc|simt select explicitly for A/B runs).
+#define GLAMR_DEFAULT_ITER_FUSED 0
+#define GLAMR_DEFAULT_LBS_TC 0
+
 namespace glamr {
 
 constexpr int kV = GLAMR_NUM_VERTS;          // 6890

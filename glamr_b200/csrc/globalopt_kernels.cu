@@ -690,7 +690,7 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   st->kpg = (KpGrad*)(b + o_kpg);
   {
     const char* e = getenv("GLAMR_ITER_PATH");
-    st->fused = !(e && strcmp(e, "legacy") == 0);
+    st->fused = e ? (strcmp(e, "fused") == 0) : GLAMR_DEFAULT_ITER_FUSED;
   }
   st->sc.heading = b + o_heading; st->sc.xy = b + o_xy; st->sc.traj_local = b + o_tl; st->sc.orient_base = b + o_ob;
   st->sc.trans_base = b + o_tb; st->sc.orient_world = b + o_ow; st->sc.trans_world = b + o_tw; st->sc.cam = b + o_cam;

@@ -589,7 +589,7 @@ static int g_lbs_path = -1;
 int lbs_path() {
   if (g_lbs_path < 0) {
     const char* e = getenv("GLAMR_LBS_PATH");
-    g_lbs_path = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+    g_lbs_path = e ? (strcmp(e, "tc") == 0 ? 1 : 0) : GLAMR_DEFAULT_LBS_TC;
   }
   return g_lbs_path;
 }

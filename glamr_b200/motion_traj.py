@@ -19,6 +19,7 @@ import torch
 from . import lib as L
 
 PAST, CUR, FUT, NZ = 10, 30, 10, 128
+PRIOR_GRAPH_DEFAULT = '0'
 WINDOW = PAST + CUR + FUT
 
 
@@ -42,7 +43,9 @@ class _GraphCache:
     The first call for a key runs `fn` eagerly (lazy initialisation must happen outside capture) and then captures it; if
     capture is refused the key stays on the eager path."""
 
-    def __init__(self, enabled=True, max_entries=8):
+    def __init__(self, enabled=None, max_entries=8):
+        if enabled is None:          # GLAMR_PRIOR_GRAPH=1|0; the default flips to on once verified on a B200
+            enabled = os.environ.get('GLAMR_PRIOR_GRAPH', PRIOR_GRAPH_DEFAULT) == '1'
         self.enabled, self.max_entries, self.entries = enabled, max_entries, {}
 
     def run(self, key, fn, inputs):

@@ -66,6 +66,12 @@ def test_rowop_vjps_match_autograd():
 
 
 # ------------------------------------------------------------------------------------------------ SMPL
+def _default_lbs_path():
+    import os
+    e = os.environ.get('GLAMR_LBS_PATH')
+    return (1 if e == 'tc' else 0) if e else 0        # library default (GLAMR_DEFAULT_LBS_TC in csrc/common.cuh)
+
+
 @pytest.fixture(params=['tensor_core', 'simt'])
 def lbs_path(request):
     """both implementations of the blend + skinning: the default tcgen05 3xTF32 blend GEMM + skinning kernel, and the single
@@ -73,7 +79,7 @@ def lbs_path(request):
     from glamr_b200 import lib as L
     L.check(L.load().glamr_smpl_set_lbs_path(1 if request.param == 'tensor_core' else 0), 'set_lbs_path')
     yield request.param
-    L.check(L.load().glamr_smpl_set_lbs_path(1), 'set_lbs_path')
+    L.check(L.load().glamr_smpl_set_lbs_path(_default_lbs_path()), 'set_lbs_path')
 
 
 def test_smpl_forward_matches_reference_golden(smpl_assets, lbs_path):
@@ -135,7 +141,7 @@ def test_smpl_tensor_core_and_simt_paths_agree(smpl_assets):
         L.check(L.load().glamr_smpl_set_lbs_path(path), 'set_lbs_path')
         r = smpl(global_orient=o, body_pose=p, betas=b, root_trans=t)
         outs.append((r.joints.clone(), r.vertices.clone()))
-    L.check(L.load().glamr_smpl_set_lbs_path(1), 'set_lbs_path')
+    L.check(L.load().glamr_smpl_set_lbs_path(_default_lbs_path()), 'set_lbs_path')
     dj, dv = (outs[0][0] - outs[1][0]).abs().max().item(), (outs[0][1] - outs[1][1]).abs().max().item()
     print(f'tensor-core vs SIMT: joints {dj:.2e}, vertices {dv:.2e}')
     assert dj < 5e-6 and dv < 5e-6
