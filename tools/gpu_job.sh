@@ -12,4 +12,4 @@ GLAMR_ITER_PATH=fused GLAMR_LBS_PATH=tc timeout 120 python tools/iter_breakdown.
 GLAMR_ITER_PATH=fused GLAMR_LBS_PATH=tc P=4 CFG=glamr_static_multi timeout 120 python tools/iter_breakdown.py 2>&1 | tail -1
 timeout 200 python tools/e2e_breakdown.py 200 300 > gpurun_out/e2e_breakdown_r02a.txt 2>&1; grep "wall ms" gpurun_out/e2e_breakdown_r02a.txt
 GLAMR_ITER_PATH=fused GLAMR_LBS_PATH=tc GLAMR_PRIOR_GRAPH=1 timeout 200 python tools/e2e_breakdown.py 200 300 > gpurun_out/e2e_breakdown_r02a_new.txt 2>&1; grep "wall ms" gpurun_out/e2e_breakdown_r02a_new.txt
-echo "=== 8 ncu launch list"; GLAMR_ITER_PATH=fused GLAMR_LBS_PATH=tc timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_r02a.csv python bench.py --steps 3 --warmup 3 --extras none --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | head -c 300; echo
+echo "=== 8 ncu launch list"; GLAMR_ITER_PATH=fused GLAMR_LBS_PATH=tc timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"lbs_|frame_residuals|traj_cam|pose_prep|apply_kernel|forward_pose|residuals_backward|cam_forward|camera_" -c 300 --csv --log-file gpurun_out/launches_r02a.csv python bench.py --steps 12 --warmup 3 --extras none --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | head -c 300; echo
