@@ -99,8 +99,16 @@ class StageCompiler:
         self.pose_all = torch.stack(pose_all).contiguous()
         self.beta_all = torch.stack(beta_all).contiguous()
         self.scale_all = None if scale_all[0] is None else torch.stack(scale_all).contiguous()
+        # host copies of what the per-stage weight tables are built from (visibility, keypoint scores, persons per frame):
+        # ONE device->host copy here instead of several per person and stage
+        P_, J_ = self.P, self.J
+        packed = torch.cat([torch.stack([torch.as_tensor(data['person_data'][pid]['vis_frames']).to(dev).double() for pid in self.pids]).reshape(-1),
+                            torch.stack([torch.as_tensor(data['person_data'][pid]['kp_2d_score']).to(dev).double() for pid in self.pids]).reshape(-1),
+                            torch.as_tensor(data['fr_num_persons']).to(dev).double().reshape(-1)]).cpu()
+        self.host_vis = packed[:P_ * T].reshape(P_, T) > 0.5
+        self.host_score = packed[P_ * T:P_ * T + P_ * T * J_].reshape(P_, T, J_)
         # camera-from-persons bookkeeping (global_recon_model.py:489-506)
-        npers = torch.as_tensor(data['fr_num_persons']).cpu().to(torch.int64)
+        npers = packed[P_ * T + P_ * T * J_:].to(torch.int64)
         has = npers > 0
         first = int(torch.where(has)[0][0])
         src, empty_idx, last, ne = [], [], first, 0
@@ -117,18 +125,17 @@ class StageCompiler:
         self.inv_num = _f32(torch.where(has, 1.0 / npers.clamp(min=1).float(), torch.zeros(T)), dev)
         rel = data.get('rel_transform_cam')
         if rel:
-            tgt = torch.zeros(self.P * self.P, T, 12)
+            tgt = torch.zeros(self.P * self.P, T, 12, device=dev)
             for (i, j), C in rel.items():
-                tgt[i * self.P + j] = torch.as_tensor(C).detach().cpu().float()[:, :3, :].reshape(T, 12)
-            self.rel_target = tgt.to(dev).contiguous()
+                tgt[i * self.P + j] = torch.as_tensor(C).detach().to(dev).float()[:, :3, :].reshape(T, 12)
+            self.rel_target = tgt.contiguous()
         else:
             self.rel_target = None
 
     # ------------------------------------------------------------------------------------------------ per stage
-    def _person_weights(self, d, loss_cfg):
+    def _person_weights(self, p, loss_cfg):
         T, J = self.T, self.J
-        vis = torch.as_tensor(d['vis_frames']).cpu().bool()
-        score = torch.as_tensor(d['kp_2d_score']).detach().cpu().double()
+        vis, score = self.host_vis[p], self.host_score[p]
         vis_idx = torch.where(vis)[0]
         nvis = int(vis.sum())
         kp_w, kp_dm = torch.zeros(T, J, dtype=torch.float64), torch.zeros(T, J, dtype=torch.float64)
@@ -207,11 +214,16 @@ class StageCompiler:
         # ---- persons
         persons = (L.Person * P)()
         norms = {}
-        for p, pid in enumerate(self.pids):
-            d, c, o = data['person_data'][pid], self.const[p], lay.persons[p]
-            kp_w, kp_dm, ctr_w, ctt_w, nrm = self._person_weights(d, loss_cfg)
+        host_w = torch.zeros(P, 2 * T * J + 2 * T, dtype=torch.float32)        # [kp_w | kp_dist_mask | ctr_w | ctt_w] per person
+        for p in range(P):
+            kp_w, kp_dm, ctr_w, ctt_w, nrm = self._person_weights(p, loss_cfg)
+            host_w[p] = torch.cat([kp_w.reshape(-1), kp_dm.reshape(-1), ctr_w, ctt_w]).float()
             for k, v in nrm.items():
                 norms[k] = norms.get(k, 0) + v
+        dev_w = host_w.to(dev)                                                   # one upload for all persons
+        keep.append(dev_w)
+        for p, pid in enumerate(self.pids):
+            d, c, o = data['person_data'][pid], self.const[p], lay.persons[p]
             ps = persons[p]
             ps.start, ps.len = c['start'], c['len']
             ps.off_xy, ps.off_heading, ps.off_dxy, ps.off_dheading = o['xy'], o['heading'], o['dxy'], o['dheading']
@@ -220,9 +232,9 @@ class StageCompiler:
             for name in ['traj_local_pred', 'orient_base_init', 'trans_base_init', 'cam_K', 'kp_target', 'orient_cam_6d',
                          'trans_cam', 'person2cam', 'dheading_mask', 'rot_mask', 'vis']:
                 setattr(ps, name, None if c[name] is None else c[name].data_ptr())
-            w = [_f32(x, dev) for x in (kp_w, kp_dm, ctr_w, ctt_w)]
-            keep += w
-            ps.kp_w, ps.kp_dist_mask, ps.ctr_w, ps.ctt_w = [x.data_ptr() for x in w]
+            base = dev_w.data_ptr() + p * dev_w.shape[1] * 4
+            ps.kp_w, ps.kp_dist_mask = base, base + T * J * 4
+            ps.ctr_w, ps.ctt_w = base + 2 * T * J * 4, base + (2 * T * J + T) * 4
         persons_dev = torch.frombuffer(bytearray(bytes(persons)), dtype=torch.uint8).to(dev)
         keep.append(persons_dev)
         pb.persons = persons_dev.data_ptr()
@@ -234,8 +246,7 @@ class StageCompiler:
             n_rel = 0
             for (i, j) in data['rel_transform_cam'].keys():
                 n_rel += T
-                both = torch.as_tensor(data['person_data'][self.pids[i]]['vis_frames']).cpu() & \
-                    torch.as_tensor(data['person_data'][self.pids[j]]['vis_frames']).cpu()
+                both = self.host_vis[i] & self.host_vis[j]
                 if both.sum() == 0:
                     continue
                 f0 = int(torch.where(both)[0][0])

@@ -386,12 +386,14 @@ class GlobalReconOptimizer:
         hvec = G.heading_to_vec(G.get_heading(q))
         d6 = G.quat_to_rot6d(G.deheading_quat(q, hq))
         n = vis_frames.shape[0]
-        vis_ind = torch.where(vis_frames)[0].cpu().numpy()
-        grid = np.arange(n, dtype=np.float32)
-        f = interp1d(vis_ind, hvec.cpu().numpy(), axis=0, assume_sorted=True, fill_value='extrapolate')
-        hvec_i = torch.tensor(f(grid), device=self.device, dtype=torch.float32)
-        f = interp1d(vis_ind, d6.cpu().numpy(), axis=0, assume_sorted=True, fill_value='extrapolate')
-        d6_i = torch.tensor(f(grid), device=self.device, dtype=torch.float32)
+        if int(vis_frames.sum()) == n:
+            hvec_i, d6_i = hvec, d6             # every frame is a sample point: linear interpolation returns the samples
+        else:
+            packed = torch.cat([hvec, d6], dim=-1).cpu().numpy()          # one device->host copy for both interpolants
+            vis_ind = np.where(vis_frames.cpu().numpy())[0]
+            f = interp1d(vis_ind, packed, axis=0, assume_sorted=True, fill_value='extrapolate')
+            both = torch.tensor(f(np.arange(n, dtype=np.float32)), device=self.device, dtype=torch.float32)
+            hvec_i, d6_i = both[:, :2].contiguous(), both[:, 2:].contiguous()
         out = G.quat_mul(G.heading_to_quat(G.vec_to_heading(hvec_i)), G.rot6d_to_quat(d6_i))
         return G.quat_mul(out, base.expand_as(out))
 
