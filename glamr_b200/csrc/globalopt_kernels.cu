@@ -265,6 +265,23 @@ __global__ void __launch_bounds__(kScanThreads) traj_cam_backward_kernel(OptCtx 
   }
 }
 
+// Stand-alone sum all-reduce of `count` floats over the peer buffers (same push-then-poll protocol and epoch counter as the
+// reduction inside apply_kernel): buf <- sum over ranks, identical bits on every rank.
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerCtx pc, float* __restrict__ buf, int count, unsigned int* ticket) {
+  const uint32_t epoch = reinterpret_cast<const uint32_t*>(pc.bufs[pc.rank])[1] + 1u;
+  const size_t row = peer_row(pc, epoch, pc.rank);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(buf[i]);
+    for (int r = 0; r < pc.world; ++r) st_peer_u64(pc.bufs[r] + row + i, w);
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    float g = 0.0f;
+    for (int r = 0; r < pc.world; ++r) g += peer_take(pc, epoch, r, i);
+    buf[i] = g;
+  }
+  if (grid_last_block(ticket) && threadIdx.x == 0) reinterpret_cast<uint32_t*>(pc.bufs[pc.rank])[1] = epoch;
+}
+
 struct AdamState {
   float* m;
   float* v;
@@ -935,6 +952,17 @@ extern "C" int glamr_opt_set_peers(glamr_opt_t* st, int rank, int world, void* c
     if (!bufs[r]) return GLAMR_EINVAL;
     st->peer.bufs[r] = (unsigned long long*)bufs[r];
   }
+  return GLAMR_OK;
+}
+
+extern "C" int glamr_allreduce_inplace(glamr_opt_t* st, float* buf, size_t count, void* stream) {
+  if (!st || !buf) return GLAMR_EINVAL;
+  if (st->peer.world <= 1) return GLAMR_OK;     // single rank: the sum is the input
+  if (count > st->peer.slot_elems) return GLAMR_ENOSPACE;
+  if (count == 0) return GLAMR_OK;
+  const int blocks = (int)((count + 255) / 256);
+  peer_allreduce_kernel<<<blocks < 592 ? blocks : 592, 256, 0, (cudaStream_t)stream>>>(st->peer, buf, (int)count, st->tickets + 3);
+  GLAMR_LAUNCH_CHECK();
   return GLAMR_OK;
 }
 

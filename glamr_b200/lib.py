@@ -108,6 +108,7 @@ def load():
     lib.glamr_peer_close.argtypes = [_vp]
     lib.glamr_peer_free.argtypes = [_vp]
     lib.glamr_opt_set_peers.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp]
+    lib.glamr_allreduce_inplace.argtypes = [_vp, _vp, ctypes.c_size_t, _vp]
     lib.glamr_opt_apply.argtypes = [_vp, _vp, _vp, ctypes.c_double, _vp, ctypes.c_int, _vp]
     lib.glamr_opt_iterate.argtypes = [_vp, _vp, _vp, ctypes.c_double, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
     if lib.glamr_sizeof_person() != ctypes.sizeof(Person) or lib.glamr_sizeof_problem() != ctypes.sizeof(Problem):

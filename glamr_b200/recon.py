@@ -591,8 +591,11 @@ class GlobalReconOptimizer:
 
     def _backward(self):
         L.check(self._lib.glamr_opt_backward(self._opt, L.ptr(self._theta), L.ptr(self._reduce), L.stream_ptr()), 'glamr_opt_backward')
-        if self.world > 1:
-            torch.distributed.all_reduce(self._reduce)        # the one collective of the path: packed gradient + term sums
+        if self.world > 1:                                     # the one collective of the path: packed gradient + term sums
+            if getattr(self, '_peer_ok', False):              # one-shot NVLink all-reduce of the library (no NCCL call)
+                L.check(self._lib.glamr_allreduce_inplace(self._opt, L.ptr(self._reduce), self._reduce.numel(), L.stream_ptr()), 'glamr_allreduce_inplace')
+            else:
+                torch.distributed.all_reduce(self._reduce)
 
     def launches_per_iteration(self):
         """kernels of the CUDA library launched per optimiser iteration for the current stage (excludes the NCCL kernel)"""

@@ -282,6 +282,11 @@ int glamr_peer_close(void* dev_ptr);      /* a pointer from glamr_peer_open */
 int glamr_peer_free(void* dev_ptr);       /* a pointer from glamr_peer_alloc */
 size_t glamr_opt_peer_bytes(const glamr_opt_t* st);
 int glamr_opt_set_peers(glamr_opt_t* st, int rank, int world, void* const* bufs /* [world], own buffer included */);
+/* buf[0..count) <- element-wise sum over all ranks, in place, over the registered peer buffers (one kernel: every thread pushes
+ * its elements to every rank, then polls its own buffer; count <= glamr_opt_reduce_count).  Collective: every rank calls it at the
+ * same point of its stream order.  No-op for a single rank.  (SURVEY.md 8b `allreduce_inplace`; the per-iteration reduction of
+ * glamr_opt_iterate is the same protocol fused into the Adam kernel.) */
+int glamr_allreduce_inplace(glamr_opt_t* st, float* buf, size_t count, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Evaluation  --  stands behind global_recon/utils/evaluator.py:202-327 (Evaluator.prepare_seq).
