@@ -332,6 +332,20 @@ GLAMR_HD void kp_joint_terms(const OptCtx& c, int p, int t, int k, const float* 
   }
 }
 
+// quat_angle_diff(a, b) (lib/utils/torch_transform.py:48-60): angle = acos(clamp(2 w^2 - 1, -1 + 1e-6, 1 - 1e-6)) with w the scalar part
+// of a (x) conj(b), i.e. the dot product of the two quaternions; also d(angle)/d(w) (0 where the clamp is active).
+GLAMR_HD void quat_angle_dot(const float* a, const float* b, float& angle, float& dangle_dw) {
+  // Near-identical rotations sit at the clamp, where acos amplifies the last bits of w: in float32 the angle of consecutive frames
+  // carries ~0.5 % noise in ANY evaluation order (the reference's own float32 value is 0.3 % off its float64 value on the test
+  // tracks); the plain dot product is the most accurate form.
+  const float w = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+  const float u = 2.0f * w * w - 1.0f;
+  const float lo = -1.0f + 1e-6f, hi = 1.0f - 1e-6f;
+  const float uc = fminf(fmaxf(u, lo), hi);
+  angle = acosf(uc);
+  dangle_dw = (u > lo && u < hi) ? -4.0f * w / sqrtf(1.0f - uc * uc) : 0.0f;
+}
+
 // Everything of frame-person (p,t) that is not per joint, given the summed joint contributions `kg`.
 GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAcc& acc) {
   const glamr_problem_t& pb = c.pb;
@@ -369,7 +383,28 @@ GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAc
 #pragma unroll
     for (int k = 0; k < 3; ++k) { c.sc.orient_ciw[n * 3 + k] = a[k]; c.sc.trans_ciw[n * 3 + k] = tcw[k]; }
     const float wr = ps.ctr_w[t];
-    if (wr != 0.0f) {
+    if (wr != 0.0f && pb.cam_traj_rot_quat) {
+      // rot_type 'quat' (loss_func.py:158-161): diff = quat_angle_diff(q(smpl_orient_cam), q(smpl_orient_cam_in_world))
+      float q1[4], dd, dw;
+      aa_to_quat(a, q1);
+      const float* qt = ps.orient_cam_q + (size_t)t * 4;
+      quat_angle_dot(qt, q1, dd, dw);
+      acc.v[GLAMR_T_CAM_TRAJ_ROT] += (double)(wr * dd * dd);
+      const float gsr = c.gs[GLAMR_T_CAM_TRAJ_ROT];
+      if (gsr != 0.0f) {
+        const float gw = 2.0f * gsr * wr * dd * dw;          // dL/d(dot)
+        const float gq[4] = {gw * qt[0], gw * qt[1], gw * qt[2], gw * qt[3]};
+        float ga[3], gM[9], t1[9], gRw[9], g[3];
+        aa_to_quat_vjp(a, gq, ga);
+        rotmat_to_aa_vjp(M, ga, gM);
+        mat3_mult(gM, Rw, t1);        // dL/dRc = gM Rw^T
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g_Rc[k] += t1[k];
+        mat3_tmul(Rc, gM, gRw);       // dL/dRw = Rc^T gM
+        aa_to_rotmat_vjp(ow, gRw, g);
+        g_ow[0] += g[0]; g_ow[1] += g[1]; g_ow[2] += g[2];
+      }
+    } else if (wr != 0.0f) {
       float Ra[9], r6[6], diff[6];
       aa_to_rotmat(a, Ra);
       rotmat_to_rot6d(Ra, r6);
@@ -419,7 +454,34 @@ GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAc
   float g_Rw[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool any_Rw = false;
   // ---- trajectory smoothness over ALL frames of the person (loss_func.py:117-144)
-  if (pb.term_enabled[GLAMR_T_TRAJ_ROT_SMOOTH]) {
+  if (pb.term_enabled[GLAMR_T_TRAJ_ROT_SMOOTH] && pb.traj_rot_smooth_quat) {
+    // rot_type 'quat' (loss_func.py:126-128): (30 * quat_angle_diff(q[t+1], q[t]))^2 per frame pair
+    const float gsm = c.gs[GLAMR_T_TRAJ_ROT_SMOOTH];
+    float q0[4], gq[4] = {0, 0, 0, 0};
+    aa_to_quat(ow, q0);
+    if (t + 1 < T) {
+      float qn[4], dd, dw;
+      aa_to_quat(ow + 3, qn);
+      quat_angle_dot(qn, q0, dd, dw);
+      acc.v[GLAMR_T_TRAJ_ROT_SMOOTH] += (double)(kFps2 * dd * dd);
+      const float gw = 2.0f * kFps2 * gsm * dd * dw;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gq[k] += gw * qn[k];
+    }
+    if (t > 0) {
+      float qp[4], dd, dw;
+      aa_to_quat(ow - 3, qp);
+      quat_angle_dot(q0, qp, dd, dw);
+      const float gw = 2.0f * kFps2 * gsm * dd * dw;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gq[k] += gw * qp[k];
+    }
+    if (gsm != 0.0f) {
+      float g[3];
+      aa_to_quat_vjp(ow, gq, g);
+      g_ow[0] += g[0]; g_ow[1] += g[1]; g_ow[2] += g[2];
+    }
+  } else if (pb.term_enabled[GLAMR_T_TRAJ_ROT_SMOOTH]) {
     float r6[6], rp[6], rn[6], R2[9];
     rotmat_to_rot6d(Rw, r6);
     float g6[6] = {0, 0, 0, 0, 0, 0};

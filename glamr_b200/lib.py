@@ -43,13 +43,13 @@ class Person(ctypes.Structure):
                  'off_world_dheading', 'off_orient_res', 'off_trans_res', 'pad_']] + \
                [(n, _vp) for n in
                 ['traj_local_pred', 'orient_base_init', 'trans_base_init', 'cam_K', 'kp_target', 'orient_cam_6d',
-                 'trans_cam', 'person2cam', 'dheading_mask', 'rot_mask', 'vis', 'kp_w', 'kp_dist_mask', 'ctr_w', 'ctt_w']]
+                 'orient_cam_q', 'trans_cam', 'person2cam', 'dheading_mask', 'rot_mask', 'vis', 'kp_w', 'kp_dist_mask', 'ctr_w', 'ctt_w']]
 
 
 class Problem(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ['P', 'T', 'J', 'cam_mode', 'off_cam_rot', 'off_cam_trans', 'use_world_res', 'has_world_dheading',
-                 'trans_res_all', 'cam_up_first_only', 'n_params', 'n_begin', 'n_end', 'owner', 'pad0_', 'pad_']] + \
+                 'trans_res_all', 'cam_up_first_only', 'n_params', 'n_begin', 'n_end', 'owner', 'cam_traj_rot_quat', 'traj_rot_smooth_quat']] + \
                [('cam_up_first_weight', ctypes.c_float), ('rel_trans_weight', ctypes.c_float),
                 ('term_weight', ctypes.c_float * NUM_TERMS), ('term_norm', ctypes.c_float * NUM_TERMS),
                 ('term_enabled', ctypes.c_int32 * NUM_TERMS), ('term_monitor', ctypes.c_int32 * NUM_TERMS)] + \

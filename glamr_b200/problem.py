@@ -62,7 +62,7 @@ def _f32(x, device):
 class StageCompiler:
     """Holds the per-person constant tensors and builds a ``Problem`` for every stage."""
 
-    def __init__(self, data, layout, flags, device, aa_to_rot6d, num_joints=26):
+    def __init__(self, data, layout, flags, device, aa_to_rot6d, num_joints=26, aa_to_quat=None):
         """flags: dict with flag_fixed_cam, flag_opt_cam, flag_opt_cam_from_person_pose, flag_cam_inv_trans_res_all,
         flag_opt_vis_local_rot, cam_fix_frames.  aa_to_rot6d: callable (device math lives in the CUDA library)."""
         self.data, self.layout, self.flags, self.device, self.J = data, layout, flags, device, num_joints
@@ -86,6 +86,7 @@ class StageCompiler:
                 'cam_K': _f32(d['cam_K'], dev).reshape(T, 9),
                 'kp_target': _f32(d['kp_2d_aligned'], dev),
                 'orient_cam_6d': _f32(aa_to_rot6d(_f32(d['smpl_orient_cam'], dev)), dev),
+                'orient_cam_q': None if aa_to_quat is None else _f32(aa_to_quat(_f32(d['smpl_orient_cam'], dev)), dev),
                 'trans_cam': _f32(d['root_trans_cam'], dev),
                 'person2cam': _f32(d['person2cam'], dev)[:, :3, :].reshape(T, 12).contiguous(),
                 'dheading_mask': _f32(mask, dev),
@@ -162,8 +163,8 @@ class StageCompiler:
             norms['kp_2d_dist'] = float(m.sum())
         if 'cam_traj_rot' in loss_cfg:                                       # loss_func.py:147-172
             sp = loss_cfg['cam_traj_rot']
-            if sp.get('rot_type', '6d') != '6d':
-                raise NotImplementedError("cam_traj_rot: only rot_type '6d' is implemented in the CUDA path")
+            if sp.get('rot_type', '6d') not in ('6d', 'quat'):
+                raise ValueError(f"cam_traj_rot: unknown rot_type {sp.get('rot_type')}")
             if sp.get('first_frame_only', False):
                 ctr_w[vis_idx[0]] = 1.0
                 norms['cam_traj_rot'] = 1
@@ -230,7 +231,7 @@ class StageCompiler:
             ps.off_z, ps.off_rot, ps.off_world_dheading = o['z'], o['rot'], o['world_dheading']
             ps.off_orient_res, ps.off_trans_res = o['orient_res'], o['trans_res']
             for name in ['traj_local_pred', 'orient_base_init', 'trans_base_init', 'cam_K', 'kp_target', 'orient_cam_6d',
-                         'trans_cam', 'person2cam', 'dheading_mask', 'rot_mask', 'vis']:
+                         'orient_cam_q', 'trans_cam', 'person2cam', 'dheading_mask', 'rot_mask', 'vis']:
                 setattr(ps, name, None if c[name] is None else c[name].data_ptr())
             base = dev_w.data_ptr() + p * dev_w.shape[1] * 4
             ps.kp_w, ps.kp_dist_mask = base, base + T * J * 4
@@ -275,8 +276,10 @@ class StageCompiler:
             'cam_inv_rot_smoothness': T - 1, 'cam_origin_smoothness': T - 1, 'cam_rot_smoothness': T - 1, 'cam_trans_smoothness': T - 1,
             'cam_depth_smoothness': 1,          # loss_func.py:102 sums over the T-1 frame pairs (the .mean() sees a 0-d tensor)
         })
-        if 'traj_rot_smoothness' in loss_cfg and loss_cfg['traj_rot_smoothness'].get('rot_type', '6d') != '6d':
-            raise NotImplementedError("traj_rot_smoothness: only rot_type '6d' is implemented in the CUDA path")
+        pb.cam_traj_rot_quat = int(loss_cfg.get('cam_traj_rot', {}).get('rot_type', '6d') == 'quat')
+        pb.traj_rot_smooth_quat = int(loss_cfg.get('traj_rot_smoothness', {}).get('rot_type', '6d') == 'quat')
+        if (pb.cam_traj_rot_quat or pb.traj_rot_smooth_quat) and self.const[0]['orient_cam_q'] is None:
+            raise ValueError("rot_type 'quat' needs the aa_to_quat callable (StageCompiler(..., aa_to_quat=...))")
         if 'cam_up_reg' in loss_cfg:
             sp = loss_cfg['cam_up_reg']
             pb.cam_up_first_weight = sp.get('first_frame_weight', 1.0)

@@ -488,7 +488,8 @@ class GlobalReconOptimizer:
         self._layout = PB.make_layout(data, self._flags)
         self._theta = torch.zeros(self._layout.n_params, device=self.device)
         PB.bind_variables(data, self._layout, self._theta)
-        self._comp = PB.StageCompiler(data, self._layout, self._flags, self.device, G.angle_axis_to_rot6d, num_joints=self.smpl.num_joints)
+        self._comp = PB.StageCompiler(data, self._layout, self._flags, self.device, G.angle_axis_to_rot6d, num_joints=self.smpl.num_joints,
+                                      aa_to_quat=G.angle_axis_to_quaternion)
         self._reduce = torch.zeros(self._layout.n_params + NUM_TERMS, device=self.device)
         self._terms = torch.zeros(NUM_TERMS + 1, device=self.device)
         self._stage_key = None

@@ -157,6 +157,7 @@ typedef struct glamr_person {
   const float* cam_K;              /* [T,9]                                                                       */
   const float* kp_target;          /* [T,J,2] kp_2d_aligned                                                       */
   const float* orient_cam_6d;      /* [T,6]  rot6d(R(smpl_orient_cam)), target of cam_traj_rot                    */
+  const float* orient_cam_q;       /* [T,4]  angle_axis_to_quaternion(smpl_orient_cam): target when rot_type 'quat' */
   const float* trans_cam;          /* [T,3]  root_trans_cam                                                       */
   const float* person2cam;         /* [T,12] 3x4, used by GLAMR_CAM_FROM_PERSONS                                  */
   const float* dheading_mask;      /* [len-1] (cam_fix_frames)                                                    */
@@ -180,7 +181,8 @@ typedef struct glamr_problem {
   int32_t n_begin, n_end;          /* frame-persons n = p*T + t whose SMPL / per-frame residuals this rank evaluates
                                     * (multi-GPU shard; any contiguous range, a person may straddle two ranks)         */
   int32_t owner;                   /* != 0: this rank also evaluates the replicated terms (camera, regs, rel)    */
-  int32_t pad0_, pad_;             /* (every iteration evaluates the full LBS; there is no reduced mode)          */
+  int32_t cam_traj_rot_quat;       /* cam_traj_rot: rot_type 'quat' (loss_func.py:158-161) instead of '6d'          */
+  int32_t traj_rot_smooth_quat;    /* traj_rot_smoothness: rot_type 'quat' (loss_func.py:126-128)                  */
   float cam_up_first_weight;
   float rel_trans_weight;
   float term_weight[GLAMR_NUM_TERMS];   /* YAML weight, 0 if the term is absent                                  */

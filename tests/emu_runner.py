@@ -24,7 +24,7 @@ class EmuRunner:
         self.layout = PB.make_layout(data, self.flags)
         self.theta = torch.zeros(self.layout.n_params)
         PB.bind_variables(data, self.layout, self.theta)
-        self.comp = PB.StageCompiler(data, self.layout, self.flags, 'cpu', rt.aa_to_rot6d)
+        self.comp = PB.StageCompiler(data, self.layout, self.flags, 'cpu', rt.aa_to_rot6d, aa_to_quat=rt.aa_to_quat)
         self.lib = hh.lib()
         self.h = None
         self.reduce = torch.zeros(self.layout.n_params + L.NUM_TERMS)

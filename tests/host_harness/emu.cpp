@@ -106,6 +106,7 @@ int glamr_host_emu_buffer(EmuHandle* h, int what, float** ptr, size_t* count) {
     case GLAMR_R_CAM_POSE_INV: *ptr = h->sc.cam_inv; *count = 12 * T; break;
     case GLAMR_R_JOINTS_WORLD: *ptr = h->sc.joints_world; *count = N * J * 3; break;
     case GLAMR_R_TRAJ_LOCAL: *ptr = h->sc.traj_local; *count = 11 * N; break;
+    case 100: *ptr = h->sc.g_orient; *count = 3 * N; break;      // test-only: dL/d smpl_orient_world of the last backward
     default: return -1;
   }
   return 0;

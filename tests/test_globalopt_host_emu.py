@@ -65,7 +65,25 @@ def test_cam_depth_smoothness_term(name, smpl_assets):
     _check_case(name, smpl_assets, mutate=add_term)
 
 
-def _check_case(name, smpl_assets, mutate=None):
+def _quat_rot_type(cfg):
+    for st in cfg.opt_stage_specs.values():
+        for k in ['cam_traj_rot', 'traj_rot_smoothness']:
+            if k in st['loss_cfg']:
+                st['loss_cfg'][k] = dict(st['loss_cfg'][k], rot_type='quat')
+
+
+@pytest.mark.parametrize('name', ['static_p1_t24', 'h36m_p1_t48_gaps'])
+def test_quaternion_rot_type_terms(name, smpl_assets):
+    """rot_type 'quat' of cam_traj_rot / traj_rot_smoothness (loss_func.py:126-128,158-161).  acos(2 w^2 - 1) of nearly equal
+    consecutive orientations is ill-conditioned in float32 (the oracle's own float32 value differs from its float64 value by
+    0.3 % on these tracks), hence the looser value tolerance for these two terms.  The reference clamps the cosine at 1 - 1e-6,
+    i.e. the gradient of a frame pair switches off below 1.41e-3 rad: on tracks that contain a pair AT that angle (the other
+    golden cases do) float32 and float64 evaluations of the reference itself disagree on the switch, so those cases cannot
+    pin the gradient; the formula was checked against float64 autograd pair by pair (max relative error 6e-14)."""
+    _check_case(name, smpl_assets, mutate=_quat_rot_type, loose_terms={'traj_rot_smoothness': 2e-2, 'cam_traj_rot': 2e-2})
+
+
+def _check_case(name, smpl_assets, mutate=None, loose_terms=None):
     gold, cfg, in_dict = case_setup(name, smpl_assets)
     if mutate is not None:
         mutate(cfg)
@@ -87,8 +105,9 @@ def _check_case(name, smpl_assets, mutate=None):
         g_all, terms = run.backward()
         for k, v in uw.items():
             got = float(terms[L.TERM_INDEX[k]])
-            assert abs(got - v) <= 2e-4 * max(abs(v), 1e-3) + 1e-7, f'{stage} term {k}: {got} vs {v}'
-        assert abs(float(terms[-1]) - total) <= 2e-4 * abs(total) + 1e-6
+            rtol = (loose_terms or {}).get(k, 2e-4)
+            assert abs(got - v) <= rtol * max(abs(v), 1e-3) + 1e-7, f'{stage} term {k}: {got} vs {v}'
+        assert abs(float(terms[-1]) - total) <= (2e-4 if not loose_terms else 2e-3) * abs(total) + 1e-6
         views = _param_views(run, data_e, ora2, specs['opt_variables'])
         assert len(views) == len(params)
         for i, (gv, gr) in enumerate(zip(views, grads)):
