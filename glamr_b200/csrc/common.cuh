@@ -31,6 +31,7 @@
 // tests passed on a B200 (GLAMR_ITER_PATH=fused|legacy, GLAMR_LBS_PATH=tc|simt select explicitly for A/B runs).
 #define GLAMR_DEFAULT_ITER_FUSED 0
 #define GLAMR_DEFAULT_LBS_TC 0
+#define GLAMR_DEFAULT_NET_WIMG 0       /* prior-network GEMMs: weight operand as a pre-split image fetched by bulk TMA (GLAMR_NET_WIMG=1) */
 
 namespace glamr {
 

@@ -125,7 +125,7 @@ __device__ __forceinline__ float4 tc_load_row4(const float* __restrict__ P, int 
   for (int q = 0; q < 4; ++q) a[q] = (row < nrows && k + q < K) ? P[(size_t)row * ld + k + q] : 0.0f;
   return make_float4(a[0], a[1], a[2], a[3]);
 }
-template <int NT, bool VEC>
+template <int NT, bool VEC, bool WIMG = false>
 __device__ __forceinline__ void tc_load_tiles(TcRegs<NT>& r, int tid, int M, int N, int K, const float* __restrict__ X, int ldx,
                                               const float* __restrict__ W, int m0, int n0, int k0) {
 #pragma unroll
@@ -133,14 +133,16 @@ __device__ __forceinline__ void tc_load_tiles(TcRegs<NT>& r, int tid, int M, int
     const int idx = tid + i * kTcThreads;
     r.x[i] = tc_load_row4<VEC>(X, ldx, m0 + (idx & (TCM - 1)), M, k0 + (idx / TCM) * 4, K);      // row, 16-byte K group (0..7)
   }
+  if (!WIMG) {
 #pragma unroll
-  for (int i = 0; i < TcCfg<NT>::kWVec; ++i) {
-    const int idx = tid + i * kTcThreads;
-    r.w[i] = tc_load_row4<VEC>(W, K, n0 + (idx & (NT - 1)), N, k0 + (idx / NT) * 4, K);
+    for (int i = 0; i < TcCfg<NT>::kWVec; ++i) {
+      const int idx = tid + i * kTcThreads;
+      r.w[i] = tc_load_row4<VEC>(W, K, n0 + (idx & (NT - 1)), N, k0 + (idx / NT) * 4, K);
+    }
   }
 }
 // split into tf32 hi / lo and store as K-major 8x16-byte core matrices (the layout umma_desc_kmajor_noswizzle describes)
-template <int NT>
+template <int NT, bool WIMG = false>
 __device__ __forceinline__ void tc_store_tiles(float* st, int tid, const TcRegs<NT>& r) {
   float* Ahi = st;
   float* Alo = st + kTcATileFloats;
@@ -155,14 +157,39 @@ __device__ __forceinline__ void tc_store_tiles(float* st, int tid, const TcRegs<
     *reinterpret_cast<float4*>(Ahi + off) = hi;
     *reinterpret_cast<float4*>(Alo + off) = lo;
   }
+  if (!WIMG) {
 #pragma unroll
-  for (int i = 0; i < TcCfg<NT>::kWVec; ++i) {
-    const int idx = tid + i * kTcThreads;
-    const int off = ((idx / NT) * NT + (idx & (NT - 1))) * 4;
-    float4 lo;
-    const float4 hi = split_tf32_4(r.w[i], lo);
-    *reinterpret_cast<float4*>(Bhi + off) = hi;
-    *reinterpret_cast<float4*>(Blo + off) = lo;
+    for (int i = 0; i < TcCfg<NT>::kWVec; ++i) {
+      const int idx = tid + i * kTcThreads;
+      const int off = ((idx / NT) * NT + (idx & (NT - 1))) * 4;
+      float4 lo;
+      const float4 hi = split_tf32_4(r.w[i], lo);
+      *reinterpret_cast<float4*>(Bhi + off) = hi;
+      *reinterpret_cast<float4*>(Blo + off) = lo;
+    }
+  }
+}
+
+// ---- weights as a pre-split operand image -------------------------------------------------------------------------
+// A weight matrix W [N,K] is constant between glamr_net_set_tensor calls: it is split into tf32 hi / lo and tiled ONCE into the
+// shared-memory image the MMA reads, [N tile][K step of 32][hi | lo][8 K groups][NT rows][4] (zero padded), so that the kernel
+// fetches the W half of a pipeline stage with one 1-D bulk TMA copy instead of loading, splitting and storing it with all threads
+// on every launch.
+template <int NT>
+__global__ void build_w_image_kernel(const float* __restrict__ W, int N, int K, int ksteps, float* __restrict__ img) {
+  const size_t total = (size_t)((N + NT - 1) / NT) * ksteps * NT * TCK;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(e % TCK);
+    const int r = (int)((e / TCK) % NT);
+    const size_t tile = e / ((size_t)TCK * NT);              // tn * ksteps + ks
+    const int ks = (int)(tile % ksteps), tn = (int)(tile / ksteps);
+    const int n = tn * NT + r, k = ks * TCK + kk;
+    const float v = (n < N && k < K) ? W[(size_t)n * K + k] : 0.0f;
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    float* q = img + tile * (2 * TcCfg<NT>::kBTileFloats) + ((size_t)(kk >> 2) * NT + r) * 4 + (kk & 3);
+    q[0] = hi;
+    q[TcCfg<NT>::kBTileFloats] = lo;
   }
 }
 
@@ -171,15 +198,17 @@ __device__ __forceinline__ void tc_store_tiles(float* st, int tid, const TcRegs<
 // loads of step it+2 in flight in registers, so the L2 latency never sits on the critical path of these small GEMMs.
 // NT = 128: 128x128 tiles (one CTA per SM).  NT = 32: 128x32 tiles for problems one tile high (M <= 128, a single
 // 120-frame window): 4x more CTAs, each with a quarter of the W traffic, split work and epilogue.
-template <int ACT, bool VEC, int NT>
+// WIMG: W points at the pre-split operand image of the weight (build_w_image_kernel) and arrives by bulk TMA (wbar[s]).
+template <int ACT, bool VEC, int NT, bool WIMG>
 __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, int N, int K, const float* __restrict__ X, int ldx,
                                                                          const float* __restrict__ W, const float* __restrict__ bias,
                                                                          const float* __restrict__ bias2, float* __restrict__ Y, int ldy) {
   using Cfg = TcCfg<NT>;
   extern __shared__ __align__(128) unsigned char tc_smem[];
   float* stage0 = reinterpret_cast<float*>(tc_smem);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + kTcStages * Cfg::kStageFloats);   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + kTcStages * Cfg::kStageFloats);   // [2] MMA completion per stage
+  uint64_t* wbar = bar + 2;                                                              // [2] weight image landed (WIMG)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * TCM, n0 = blockIdx.x * NT;
 
@@ -187,17 +216,25 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(NT));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  const int nk = (K + TCK - 1) / TCK;
+  constexpr uint32_t kWBytes = 2 * Cfg::kBTileFloats * sizeof(float);
+  const float* wimg = W + (size_t)blockIdx.x * nk * (2 * Cfg::kBTileFloats);            // this column tile's K steps, contiguous
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&wbar[0], 1);
+    mbar_init(&wbar[1], 1);
     mbar_fence_init();
+    if (WIMG) {
+      mbar_expect_tx(&wbar[0], kWBytes);
+      tma_bulk_g2s(stage0 + 2 * kTcATileFloats, wimg, kWBytes, &wbar[0]);
+    }
   }
-  const int nk = (K + TCK - 1) / TCK;
   const int dbg = GLAMR_DBG(g_tc_dbg);
   TcRegs<NT> regs;
-  tc_load_tiles<NT, VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, 0);
-  tc_store_tiles<NT>(stage0, tid, regs);
-  if (nk > 1) tc_load_tiles<NT, VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, TCK);
+  tc_load_tiles<NT, VEC, WIMG>(regs, tid, M, N, K, X, ldx, W, m0, n0, 0);
+  tc_store_tiles<NT, WIMG>(stage0, tid, regs);
+  if (nk > 1) tc_load_tiles<NT, VEC, WIMG>(regs, tid, M, N, K, X, ldx, W, m0, n0, TCK);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -210,6 +247,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
     const int s = it & 1;
     float* st = stage0 + s * Cfg::kStageFloats;
     if (tid == 0) {
+      if (WIMG) mbar_wait(&wbar[s], (it >> 1) & 1);                       // this stage's weight image has landed
 #pragma unroll
       for (int k8 = 0; k8 < ((dbg & 1) ? 0 : TCK / 8); ++k8) {           // one tf32 MMA consumes K = 8 (two 16-byte K groups)
         const size_t koa = (size_t)k8 * 2 * TCM * 4, kob = (size_t)k8 * 2 * NT * 4;   // floats
@@ -226,8 +264,12 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tf32x3_tcgen05_kernel(int M, 
     if (it + 1 < nk) {
       // stage s^1 was consumed by the MMAs of step it-1: wait for their commit, then refill it while step `it` computes
       if (it >= 1) mbar_wait(&bar[s ^ 1], ((it - 1) >> 1) & 1);
-      if (!(dbg & 2)) tc_store_tiles<NT>(stage0 + (s ^ 1) * Cfg::kStageFloats, tid, regs);
-      if (it + 2 < nk && !(dbg & 8)) tc_load_tiles<NT, VEC>(regs, tid, M, N, K, X, ldx, W, m0, n0, (it + 2) * TCK);
+      if (WIMG && tid == 0) {                                            // stage s^1 is free: fetch the weight image of step it+1
+        mbar_expect_tx(&wbar[s ^ 1], kWBytes);
+        tma_bulk_g2s(stage0 + (s ^ 1) * Cfg::kStageFloats + 2 * kTcATileFloats, wimg + (size_t)(it + 1) * (2 * Cfg::kBTileFloats), kWBytes, &wbar[s ^ 1]);
+      }
+      if (!(dbg & 2)) tc_store_tiles<NT, WIMG>(stage0 + (s ^ 1) * Cfg::kStageFloats, tid, regs);
+      if (it + 2 < nk && !(dbg & 8)) tc_load_tiles<NT, VEC, WIMG>(regs, tid, M, N, K, X, ldx, W, m0, n0, (it + 2) * TCK);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
     }
@@ -303,26 +345,74 @@ struct ScopedFp32Gemm {
   ~ScopedFp32Gemm() { g_gemm_mode = saved; }
 };
 
+// ---- cache of weight operand images, keyed by (device pointer, N, K, tile width); cleared when a network's tensors change
+struct WImgKey {
+  const float* w; int N, K, NT;
+  bool operator<(const WImgKey& o) const { return w != o.w ? w < o.w : (N != o.N ? N < o.N : (K != o.K ? K < o.K : NT < o.NT)); }
+};
+static std::map<WImgKey, float*> g_wimg;
+static int g_wimg_enabled = -1;     // GLAMR_NET_WIMG=0|1 (default: GLAMR_DEFAULT_NET_WIMG)
+static void wimg_clear() {
+  for (auto& kv : g_wimg) cudaFree(kv.second);
+  g_wimg.clear();
+}
+template <int NT>
+static int wimg_get(cudaStream_t s, const float* W, int N, int K, const float** out) {
+  const WImgKey key{W, N, K, NT};
+  auto it = g_wimg.find(key);
+  if (it != g_wimg.end()) { *out = it->second; return GLAMR_OK; }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (cap != cudaStreamCaptureStatusNone) { *out = nullptr; return GLAMR_OK; }      // never allocate while a graph is being captured
+  const int ksteps = (K + TCK - 1) / TCK, tiles = (N + NT - 1) / NT;
+  float* img = nullptr;
+  GLAMR_CUDA_TRY(cudaMalloc(&img, (size_t)tiles * ksteps * 2 * TcCfg<NT>::kBTileFloats * sizeof(float)));
+  const size_t total = (size_t)tiles * ksteps * NT * TCK;
+  build_w_image_kernel<NT><<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, s>>>(W, N, K, ksteps, img);
+  GLAMR_LAUNCH_CHECK();
+  g_wimg[key] = img;
+  *out = img;
+  return GLAMR_OK;
+}
+
 template <int NT>
 static int gemm_tc_launch(cudaStream_t s, int M, int N, int K, const float* X, int ldx, const float* W, const float* b, const float* b2,
                           float* Y, int ldy, int act) {
   static bool attr = false;
   constexpr size_t smem = TcCfg<NT>::kSmemBytes;
   if (!attr) {
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, true, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, true, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, false, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, false, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, true, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, true, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<0, false, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_tcgen05_kernel<1, false, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
+  }
+  if (g_wimg_enabled < 0) {
+    const char* e = getenv("GLAMR_NET_WIMG");
+    g_wimg_enabled = e ? atoi(e) : GLAMR_DEFAULT_NET_WIMG;
   }
   dim3 grid((N + NT - 1) / NT, (M + TCM - 1) / TCM);
   const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)X | (uintptr_t)W) % 16 == 0);
-  if (vec) {
-    if (act == 1) gemm_tf32x3_tcgen05_kernel<1, true, NT><<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
-    else gemm_tf32x3_tcgen05_kernel<0, true, NT><<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+  const float* img = nullptr;
+  if (g_wimg_enabled) {
+    const int rc = wimg_get<NT>(s, W, N, K, &img);
+    if (rc) return rc;
+  }
+  auto go = [&](auto kernel, const float* wptr) {
+    kernel<<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, wptr, b, b2, Y, ldy);
+  };
+  if (img) {
+    const bool xvec = (K % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)X % 16 == 0);
+    if (xvec) { if (act == 1) go(gemm_tf32x3_tcgen05_kernel<1, true, NT, true>, img); else go(gemm_tf32x3_tcgen05_kernel<0, true, NT, true>, img); }
+    else { if (act == 1) go(gemm_tf32x3_tcgen05_kernel<1, false, NT, true>, img); else go(gemm_tf32x3_tcgen05_kernel<0, false, NT, true>, img); }
+  } else if (vec) {
+    if (act == 1) go(gemm_tf32x3_tcgen05_kernel<1, true, NT, false>, W); else go(gemm_tf32x3_tcgen05_kernel<0, true, NT, false>, W);
   } else {
-    if (act == 1) gemm_tf32x3_tcgen05_kernel<1, false, NT><<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
-    else gemm_tf32x3_tcgen05_kernel<0, false, NT><<<grid, kTcThreads, smem, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+    if (act == 1) go(gemm_tf32x3_tcgen05_kernel<1, false, NT, false>, W); else go(gemm_tf32x3_tcgen05_kernel<0, false, NT, false>, W);
   }
   GLAMR_LAUNCH_CHECK();
   return GLAMR_OK;
@@ -705,6 +795,8 @@ extern "C" int glamr_net_create(glamr_net** out) {
 }
 extern "C" int glamr_net_destroy(glamr_net* n) {
   if (!n) return GLAMR_OK;
+  cudaDeviceSynchronize();
+  wimg_clear();                              // operand images are keyed by weight pointers that are about to be freed
   for (void* p : n->allocs) cudaFree(p);
   delete n;
   return GLAMR_OK;
@@ -716,6 +808,7 @@ extern "C" int glamr_net_set_tensor(glamr_net* n, const char* name, const float*
   GLAMR_CUDA_TRY(cudaMalloc(&p, numel * sizeof(float)));
   GLAMR_CUDA_TRY(cudaMemcpy(p, host, numel * sizeof(float), cudaMemcpyHostToDevice));
   n->allocs.push_back(p);
+  if (n->t.count(name)) { cudaDeviceSynchronize(); wimg_clear(); }      // a weight was replaced: cached operand images are stale
   n->t[name] = {(float*)p, numel};
   return GLAMR_OK;
 }
