@@ -155,32 +155,46 @@ class CpuPort:
                                  on_iter=lambda it, last, dt: times.append(dt))
         return times
 
-    def sweep_threads(self, warm=2, probe=4):
-        """median seconds per iteration for each candidate thread count; returns (best_threads, {threads: median})"""
+    def sweep_threads(self, warm=1, probe=3, budget_s=40.0):
+        """median seconds per iteration for each candidate thread count, smallest count first; a candidate is abandoned as soon
+        as one of its iterations takes > 3x the best median so far, and the sweep stops when `budget_s` is spent (boxes exist
+        where many-thread torch CPU runs are 25x slower than 8 threads).  -> (best_threads, {threads: median})"""
         cands = sorted({t for t in (8, 16, 32, host_threads()) if t <= host_threads()})
-        res = {}
+        res, t_start = {}, time.perf_counter()
         for t in cands:
-            ts = self.time_iterations(warm + probe, threads=t)[warm:]
-            res[t] = float(np.median(ts))
+            if res and time.perf_counter() - t_start > budget_s:
+                break
+            ts = []
+            for i in range(warm + probe):
+                (dt,) = self.time_iterations(1, threads=t)
+                ts.append(dt)
+                if res and dt > 3.0 * min(res.values()):
+                    break
+            res[t] = float(np.median(ts[warm:] or ts))
         best = min(res, key=res.get)
         return best, res
 
 
-def cpu_baseline_block(assets, in_dict, cfg, units, iters, stage=None, sweep=True):
+def cpu_baseline_block(assets, in_dict, cfg, units, iters, stage=None, sweep=True, threads=None, budget_s=60.0):
+    """the CPU port on one workload, bounded by wall-clock: thread sweep (<= 40 s), then min(iters, what fits `budget_s`) timed
+    iterations but never fewer than 5"""
     port = CpuPort(assets, in_dict, cfg, stage)
-    port.time_iterations(3)                                      # first-call warm-up (allocator, threads)
+    port.time_iterations(1, threads=threads or min(8, host_threads()))       # first-call warm-up (allocator, thread pool)
     if sweep:
         threads, sweep_res = port.sweep_threads()
+        per = sweep_res[threads]
     else:
-        threads, sweep_res = host_threads(), {}
-    ts = port.time_iterations(iters, threads=threads)
+        threads, sweep_res = threads or min(8, host_threads()), {}
+        (per,) = port.time_iterations(1, threads=threads)
+    n = int(max(5, min(iters, budget_s / max(per, 1e-6))))
+    ts = port.time_iterations(n, threads=threads)
     med, best = float(np.median(ts)), float(np.min(ts))
     return {'value': units / med, 'value_best': units / best, 'unit': 'frame*person*iter/s', 'cores': threads, 'host_threads_available': host_threads(),
             'kind': 'port', 'ms_per_iter_median': med * 1e3, 'ms_per_iter_best': best * 1e3,
             'thread_sweep_ms_per_iter': {str(k): round(v * 1e3, 2) for k, v in sweep_res.items()},
             'ms_per_iter_list': [round(t * 1e3, 1) for t in ts],
-            'sample': f'{iters} timed iterations (median; best in value_best) of the oracle port (torch CPU, {threads} threads' +
-                      (' = fastest of the sweep' if sweep else '') + f') on the same workload ({port.stage}), after 3 warm-up iterations'}
+            'sample': f'{n} timed iterations (median; best in value_best) of the oracle port (torch CPU, {threads} threads' +
+                      (' = fastest of the sweep' if sweep else '') + f') on the same workload ({port.stage}), after warm-up; bounded to ~{budget_s:.0f} s'}
 
 
 def run_reference(args):
@@ -196,7 +210,7 @@ def run_reference(args):
     # too slow, fewer timed steps run (stated in `sample`).
     sample = persons
     port = CpuPort(assets, in_dict, cfg)
-    port.time_iterations(2)
+    port.time_iterations(1, threads=min(8, host_threads()))
     threads, sweep_res = port.sweep_threads(warm=1, probe=3)
     probe = sweep_res[threads]
     if probe * (K + W) > REF_BUDGET_S and persons > 1:
@@ -437,7 +451,7 @@ def multi_gpu_parity(ctx, cfg, in_dict, iters=20):
     return res
 
 
-def staged_workload(ctx, cfg_id, persons, frames, K, with_e2e=True, cpu_iters=0):
+def staged_workload(ctx, cfg_id, persons, frames, K, with_e2e=True, cpu_iters=0, cpu_threads=None):
     """a multi-stage config on one video, frame-persons sharded over the ranks: per-stage iteration times + end to end"""
     assets, in_dict, cfg = make_problem(cfg_id, persons, frames)
     units = persons * frames
@@ -464,7 +478,7 @@ def staged_workload(ctx, cfg_id, persons, frames, K, with_e2e=True, cpu_iters=0)
         res['e2e'] = {'value': units * info['iterations'] / info['seconds'], 'unit': 'frame*person*iter/s', **info,
                       'h2d_bytes': h2d, 'd2h_bytes': d2h, 'what': 'optimize(in_dict numpy) -> numpy dict incl. init_data, all YAML iterations of both stages'}
     if cpu_iters and ctx.rank == 0 and ctx.world == 1:
-        res['cpu_baseline'] = cpu_baseline_block(assets, in_dict, cfg, units, cpu_iters, stage=last, sweep=False)
+        res['cpu_baseline'] = cpu_baseline_block(assets, in_dict, cfg, units, cpu_iters, stage=last, sweep=False, threads=cpu_threads, budget_s=30.0)
     return res
 
 
