@@ -639,7 +639,12 @@ struct glamr_opt {
   size_t arena_bytes;
   float gs[GLAMR_NUM_TERMS];
   int timing;                 // != 0: bracket the LBS kernel with events (bench / roofline only, not graph-capturable)
-  cudaEvent_t ev_lbs0, ev_lbs1;
+  cudaEvent_t ev_lbs0, ev_lbs1, ev_blend0, ev_blend1;
+  // tensor-core LBS, software-pipelined: the blend GEMM of the NEXT evaluation runs on `aux` concurrently with the residual /
+  // backward kernels of this one (it depends on body pose and betas only); `vpt_ready` says the workspace holds a valid v_posed
+  cudaStream_t aux;
+  cudaEvent_t ev_fork, ev_join;
+  int vpt_ready;
   cudaEvent_t ev[24];         // timing == 2: one event after every launch of glamr_opt_backward / glamr_opt_apply
   int n_ev;
   // glamr_opt_iterate: one captured iteration (backward + apply), valid for the arguments it was captured with
@@ -729,6 +734,8 @@ extern "C" int glamr_opt_kernel_timing(glamr_opt_t* st, int enable) {
   if (enable && !st->ev_lbs0) {
     GLAMR_CUDA_TRY(cudaEventCreate(&st->ev_lbs0));
     GLAMR_CUDA_TRY(cudaEventCreate(&st->ev_lbs1));
+    GLAMR_CUDA_TRY(cudaEventCreate(&st->ev_blend0));
+    GLAMR_CUDA_TRY(cudaEventCreate(&st->ev_blend1));
     for (int i = 0; i < 24; ++i) GLAMR_CUDA_TRY(cudaEventCreate(&st->ev[i]));
   }
   st->timing = enable;
@@ -739,6 +746,12 @@ extern "C" int glamr_opt_last_lbs_ms(glamr_opt_t* st, float* ms) {
   if (!st || !ms || !st->ev_lbs0) return GLAMR_EINVAL;
   GLAMR_CUDA_TRY(cudaEventSynchronize(st->ev_lbs1));
   GLAMR_CUDA_TRY(cudaEventElapsedTime(ms, st->ev_lbs0, st->ev_lbs1));
+  if (st->vpt_ready && st->aux) {            // tensor-core path: + the blend GEMM (timed on its own stream) = the whole LBS
+    float b = 0.0f;
+    GLAMR_CUDA_TRY(cudaEventSynchronize(st->ev_blend1));
+    GLAMR_CUDA_TRY(cudaEventElapsedTime(&b, st->ev_blend0, st->ev_blend1));
+    *ms += b;
+  }
   return GLAMR_OK;
 }
 
@@ -756,7 +769,8 @@ extern "C" int glamr_opt_destroy(glamr_opt_t* st) {
   if (st && st->iter_exec) cudaGraphExecDestroy(st->iter_exec);
   if (st && st->cap_stream) cudaStreamDestroy(st->cap_stream);
   if (!st) return GLAMR_OK;
-  if (st->ev_lbs0) { cudaEventDestroy(st->ev_lbs0); cudaEventDestroy(st->ev_lbs1); for (int i = 0; i < 24; ++i) cudaEventDestroy(st->ev[i]); }
+  if (st->ev_lbs0) { cudaEventDestroy(st->ev_lbs0); cudaEventDestroy(st->ev_lbs1); cudaEventDestroy(st->ev_blend0); cudaEventDestroy(st->ev_blend1); for (int i = 0; i < 24; ++i) cudaEventDestroy(st->ev[i]); }
+  if (st->aux) { cudaStreamSynchronize(st->aux); cudaStreamDestroy(st->aux); cudaEventDestroy(st->ev_fork); cudaEventDestroy(st->ev_join); }
   cudaFree(st->arena);
   free(st);
   return GLAMR_OK;
@@ -769,6 +783,8 @@ extern "C" int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* pb,
   st->gen++;
   compute_gs(st);
   if (reset_adam & 2) {      // handle re-used for a new sequence: scratch (incl. tickets, moments) back to its initial zeros
+    if (st->aux) GLAMR_CUDA_TRY(cudaStreamSynchronize(st->aux));
+    st->vpt_ready = 0;       // new body poses: the pipelined blend has to be primed again
     GLAMR_CUDA_TRY(cudaMemsetAsync(st->arena, 0, st->arena_bytes, (cudaStream_t)stream));
     reset_adam |= 1;
   }
@@ -788,7 +804,7 @@ extern "C" int glamr_opt_launch_count(const glamr_opt_t* st, int via_iterate) {
   if (!st) return GLAMR_EINVAL;
   const bool from_persons = st->pb.cam_mode == GLAMR_CAM_FROM_PERSONS;
   const bool has_frames = st->pb.n_end > st->pb.n_begin;
-  const int fwd = 1 + (from_persons ? 1 : 0) + (has_frames ? (st->fused ? 0 : 1) + lbs_kernel_count(st->smpl) : 0);     // forward [+ cam_forward] [+ pose_prep] + lbs
+  const int fwd = 1 + (from_persons ? 1 : 0) + (has_frames ? (st->fused ? 0 : 1) + (lbs_kernel_count(st->smpl) == 2 ? 3 : 1) : 0);     // forward [+ cam_forward] [+ pose_prep] + lbs
   if (st->fused && !from_persons)                                        // fused tail; Adam inside it when glamr_opt_iterate runs a single-GPU loop
     return fwd + 1 + ((via_iterate && st->peer.world <= 1) ? 0 : 1);
   return fwd + 1 + (from_persons ? 2 : 0) + 1 + 1;                       // residuals [+ camera backward + scatter] + traj/cam backward + apply
@@ -818,13 +834,23 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   const int lpad = (pb.T + 31) & ~31;
   const size_t fwd_smem = (size_t)3 * lpad * sizeof(float);
   const bool fused_fwd = st->fused && fwd_smem <= 200 * 1024;
+  const bool tc = lbs_path() == 1 && st->smpl.tcB != nullptr;
+  SmplWorkspace wo_pose = wo;
+  if (tc) {
+    wo_pose.tcA = nullptr;                   // the features belong to blend_features_kernel (side stream); pose prep must not rewrite them
+    if (!st->aux) {
+      GLAMR_CUDA_TRY(cudaStreamCreateWithFlags(&st->aux, cudaStreamNonBlocking));
+      GLAMR_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming));
+      GLAMR_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming));
+    }
+  }
   if (fused_fwd) {
     if (fwd_smem > 48 * 1024 && st->fwd_smem_set < fwd_smem) {
       GLAMR_CUDA_TRY(cudaFuncSetAttribute(forward_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
       st->fwd_smem_set = fwd_smem;
     }
     const int chunks = (pb.T + kFwdFrames - 1) / kFwdFrames;
-    GLAMR_CUDA_TRY(launch_pdl(1, forward_pose_kernel, dim3(pb.P * chunks), dim3(kScanThreads), fwd_smem, s, c, st->smpl, wo, n_begin,
+    GLAMR_CUDA_TRY(launch_pdl(1, forward_pose_kernel, dim3(pb.P * chunks), dim3(kScanThreads), fwd_smem, s, c, st->smpl, wo_pose, n_begin,
                               from_persons ? 0 : 1, chunks, lpad));      // also zeroes reduce_buf
   } else {
     GLAMR_CUDA_TRY(launch_pdl(1, traj_cam_forward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1));   // also zeroes reduce_buf
@@ -834,16 +860,36 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
     GLAMR_CUDA_TRY(launch_pdl(1, cam_forward_kernel, dim3(st->slots_cam), dim3(kFrameThreads), 0, s, c));
   }
   GLAMR_MARK();
+  bool forked = false;
   if (n_end > n_begin) {
     const int nn = n_end - n_begin;
+    const float* pose_l = pb.smpl_pose_all + (size_t)n_begin * 69;
+    const float* beta_l = pb.smpl_beta_all + (size_t)n_begin * kNB;
     int rc;
     if (!fused_fwd)
-      if ((rc = launch_pose_prep(st->smpl, nn, st->sc.orient_world + (size_t)n_begin * 3, pb.smpl_pose_all + (size_t)n_begin * 69,
-                                 pb.smpl_beta_all + (size_t)n_begin * kNB, 1, wo, s, true))) return rc;
+      if ((rc = launch_pose_prep(st->smpl, nn, st->sc.orient_world + (size_t)n_begin * 3, pose_l, beta_l, 1, wo_pose, s, true))) return rc;
     GLAMR_MARK();
-    if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
-    if ((rc = launch_lbs(st->smpl, 0, nn, pb.smpl_beta_all + (size_t)n_begin * kNB, wo, nullptr, s, true))) return rc;
-    if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
+    if (tc) {
+      if (!st->vpt_ready) {                 // first evaluation after create / a new sequence: prime the pipeline in order
+        if ((rc = launch_blend(st->smpl, nn, pose_l, beta_l, wo, s))) return rc;
+        st->vpt_ready = 1;
+      }
+      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
+      if ((rc = launch_skin(st->smpl, nn, wo, nullptr, s))) return rc;
+      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
+      // the blend of the next evaluation: side stream, concurrent with the residual / backward kernels below
+      GLAMR_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
+      GLAMR_CUDA_TRY(cudaStreamWaitEvent(st->aux, st->ev_fork, 0));
+      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend0, st->aux));
+      if ((rc = launch_blend(st->smpl, nn, pose_l, beta_l, wo, st->aux))) return rc;
+      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend1, st->aux));
+      GLAMR_CUDA_TRY(cudaEventRecord(st->ev_join, st->aux));
+      forked = true;
+    } else {
+      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
+      if ((rc = launch_lbs(st->smpl, 0, nn, beta_l, wo, nullptr, s, true))) return rc;
+      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
+    }
     GLAMR_MARK();
   }
   if (st->fused && !from_persons) {
@@ -855,6 +901,7 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
     GLAMR_CUDA_TRY(launch_pdl(8, residuals_backward_kernel, dim3((N + kFusedFramesPerCta - 1) / kFusedFramesPerCta), dim3(kScanThreads), 0, s, c, st->smpl, wo,
                               n_begin, a));
     GLAMR_MARK();
+    if (forked) GLAMR_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join, 0));
     return GLAMR_OK;
   }
   if (adam) return GLAMR_EINVAL;               // Adam inside the backward pass exists only in the fused kernel
@@ -872,6 +919,7 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   GLAMR_CUDA_TRY(launch_pdl(16, traj_cam_backward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1, part_traj,
                             (const double*)st->partial, n_slots, reduce_buf, st->tickets, pc));
   GLAMR_MARK();
+  if (forked) GLAMR_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join, 0));      // the side stream rejoins before the evaluation ends
   return GLAMR_OK;
 }
 extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream) {

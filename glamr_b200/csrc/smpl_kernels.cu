@@ -297,6 +297,39 @@ lbs_kernel(SmplDev m, int n_begin, int n_end, const float* __restrict__ betas, S
 }
 
 
+// ------------------------------------------------------------------------------------------------ blend features
+// The A operand of the blend GEMM for frame-person f: (R_j - I) of the 23 body joints (lbs.py:256-258), the betas, the constant 1
+// that multiplies v_template and zero padding, as tf32 hi / lo in the UMMA image (see pose_prep_frame).  It depends on the body
+// pose and the betas only -- NOT on the root orientation -- so the optimiser evaluates it (and the blend GEMM behind it) off the
+// critical path of the iteration.  One warp per frame-person.
+__global__ void __launch_bounds__(128) blend_features_kernel(int n, const float* __restrict__ body_pose, const float* __restrict__ betas, SmplWorkspace w) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (f >= n) return;
+  float* tile = w.tcA + (size_t)(f >> 7) * kTcChunks * kTcAStageFloats;
+  const int r = f & 127;
+  auto put = [&](int k, float v) {
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    float* q = tile + (size_t)(k >> 3) * kTcAStageFloats + (((k >> 2) & 1) * kTcM + r) * 4 + (k & 3);
+    q[0] = hi;
+    q[kTcAStageFloats / 2] = lo;
+  };
+  if (lane >= 1 && lane < kNJ) {
+    const float* bp = body_pose + (size_t)f * 69 + (lane - 1) * 3;
+    const float rv[3] = {bp[0], bp[1], bp[2]};
+    float R[9];
+    rodrigues_smplx(rv, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) put((lane - 1) * 9 + k, R[k] - ((k % 4 == 0) ? 1.0f : 0.0f));
+  } else if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < kNB; ++l) put(kPF + l, betas ? betas[(size_t)f * kNB + l] : 0.0f);
+    put(kPF + kNB, 1.0f);
+#pragma unroll
+    for (int k = kTcFeat; k < kTcK; ++k) put(k, 0.0f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ tensor-core LBS
 // The shape blend + pose blend of SMPL is one contraction  v_posed[frame, col] = sum_k feat[frame, k] basis[col, k]
 // (k: 207 pose features x posedirs | 10 betas x shapedirs | 1 x v_template; lbs.py:240,256-267), i.e. a [n x 218] x [218 x 20670]
@@ -585,6 +618,39 @@ int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* 
 
 // pdl: launch with the programmatic-serialization attribute.  Only for callers whose betas are long-lived constants
 // (the optimiser): the kernel reads betas / shapedirs / posedirs BEFORE it waits for the preceding grid.
+static int lbs_set_attrs() {
+  static bool attrs = false;
+  if (!attrs) {
+    attrs = true;
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
+  }
+  return GLAMR_OK;
+}
+// blend features + blend GEMM for local frame-persons [0, n): v_posed (transposed) of the workspace
+int launch_blend(const SmplDev& m, int n, const float* body_pose, const float* betas, const SmplWorkspace& w, cudaStream_t s) {
+  if (n <= 0) return GLAMR_OK;
+  int rc;
+  if ((rc = lbs_set_attrs())) return rc;
+  blend_features_kernel<<<(n + 3) / 4, 128, 0, s>>>(n, body_pose, betas, w);
+  GLAMR_LAUNCH_CHECK();
+  lbs_blend_tc_kernel<<<dim3(kTcNTiles, (n + kTcM - 1) / kTcM), kTcThreads, kTcSmemBytes, s>>>(m, w);
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+// skinning of local frame-persons [0, n) from the workspace's v_posed and A
+int launch_skin(const SmplDev& m, int n, const SmplWorkspace& w, float* vertices, cudaStream_t s) {
+  if (n <= 0) return GLAMR_OK;
+  int rc;
+  if ((rc = lbs_set_attrs())) return rc;
+  dim3 grid(kNVTiles, (n + kFramesPerCta - 1) / kFramesPerCta);
+  if (m.K == 4) lbs_skin_kernel<4><<<grid, kLbsThreads, kSkinSmemBytes, s>>>(m, 0, n, w, vertices);
+  else lbs_skin_kernel<0><<<grid, kLbsThreads, kSkinSmemBytes, s>>>(m, 0, n, w, vertices);
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+
 static int g_lbs_path = -1;
 int lbs_path() {
   if (g_lbs_path < 0) {
@@ -600,13 +666,10 @@ int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, con
   if (n_end <= n_begin) return GLAMR_OK;
   if (n_begin % kFramesPerCta != 0) return GLAMR_EINVAL;   // the tile-major scratch is indexed by whole frame tiles
   dim3 grid(kNVTiles, (n_end - n_begin + kFramesPerCta - 1) / kFramesPerCta);
-  static bool attrs = false;
-  const int path = lbs_path();             // 1: tensor-core blend GEMM + skinning kernel (default), 0: the one-kernel FP32 SIMT path
-  if (!attrs) {
-    attrs = true;
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
-    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
+  const int path = lbs_path();             // 1: tensor-core blend GEMM + skinning kernel, 0: the one-kernel FP32 SIMT path
+  {
+    const int rc = lbs_set_attrs();
+    if (rc) return rc;
   }
   if (path == 1 && m.tcB && w.tcA && n_begin == 0) {
     const int mtiles = (n_end + kTcM - 1) / kTcM;

@@ -203,6 +203,9 @@ int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* 
 // n_begin..n_end: frame-person range to skin.  vertices may be NULL.
 int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices,
                cudaStream_t s, bool pdl = false);
+// tensor-core path in two halves (the optimiser pipelines them: the blend depends on body pose / betas only)
+int launch_blend(const SmplDev& m, int n, const float* body_pose, const float* betas, const SmplWorkspace& w, cudaStream_t s);
+int launch_skin(const SmplDev& m, int n, const SmplWorkspace& w, float* vertices, cudaStream_t s);
 int lbs_path();                              // 1 tensor-core blend + skinning kernels, 0 one-kernel FP32 SIMT path
 int lbs_kernel_count(const SmplDev& m);      // kernels one launch_lbs call launches
 int launch_joints_finalize(const SmplDev& m, int n, int orig_joints, const float* root_trans, const float* root_scale,
