@@ -80,6 +80,52 @@ def float64_trajectory(assets, name, cfg_id, P, T, gaps, niters, rec):
         for k in FINAL_KEYS:
             if k in pd and pd[k] is not None:
                 out[f'final64/{pid}/{k}'] = pd[k].detach().numpy()
+    out.update(perturbed_trajectory(assets, name, cfg_id, P, T, gaps, niters, rec))
+    return out
+
+
+def perturbed_trajectory(assets, name, cfg_id, P, T, gaps, niters, rec):
+    """Second yardstick: the float32 oracle started from an init state whose float tensors are perturbed by ONE float32 rounding
+    (x -> x (1 +- 2^-23), seeded signs).  Any re-implementation reaches the loop with such differences (sin/cos of another libm,
+    another summation order); Adam's m / sqrt(v) turns a relative gradient change eps into parameter changes of ~ lr * k * eps.
+    |final_pert - final| is that amplification measured on the reference's own arithmetic."""
+    from helpers import ReplayMT
+    from glamr_b200.config import Config
+    from oracle.global_opt import OracleGlobalRecon
+    cfg = Config(cfg_id)
+    for st in cfg.opt_stage_specs.values():
+        st['opt_niters'] = niters
+    in_dict = make_in_dict(assets, P, T, seed=0, gaps=gaps, seq_name=name)
+    ora = OracleGlobalRecon(cfg, assets, mt_model=ReplayMT(rec))
+    data = ora.init_data(in_dict)
+    g = torch.Generator().manual_seed(12345)
+
+    def perturb(x):
+        if isinstance(x, torch.Tensor) and x.dtype == torch.float32:
+            sign = (torch.randint(0, 2, x.shape, generator=g).float() * 2 - 1)
+            return x * (1 + sign * 2.0 ** -23)
+        if isinstance(x, dict):
+            return {k: perturb(v) for k, v in x.items()}
+        return x
+    data = perturb(data)
+    out = {}
+    for stage, specs in cfg.opt_stage_specs.items():
+        logs = []
+        ora.optimize_main(data, specs['opt_variables'], specs['opt_lr'], specs['opt_niters'], specs['loss_cfg'], {'stage': stage},
+                          on_iter=lambda it, last, dt: logs.append({k: float(v) for k, v in last['uw'].items()}))
+        if specs.get('reinitialize_cam', False):
+            from oracle import rotations as rt
+            data['cam_pose'][:] = data['cam_pose'][[0]]
+            data['cam_pose_inv'] = rt.inverse_transform(data['cam_pose'])
+        for k in logs[0]:
+            out[f'loss_pert/{stage}/{k}'] = np.asarray([l[k] for l in logs], np.float64)
+    for k in FINAL_GLOBAL_KEYS:
+        if k in data:
+            out[f'final_pert/{k}'] = data[k].detach().numpy()
+    for pid, pd in data['person_data'].items():
+        for k in FINAL_KEYS:
+            if k in pd and pd[k] is not None:
+                out[f'final_pert/{pid}/{k}'] = pd[k].detach().numpy()
     return out
 
 

@@ -62,10 +62,12 @@ def main(cases):
             if f'final64/{k}' not in gold:
                 continue
             r64, r32 = gold[f'final64/{k}'], gold[f'final/{k}']
+            rp = gold.get(f'final_pert/{k}')
             if k == 'cam_pose':
                 r64, r32, v = r64[:, :3], r32[:, :3], v[:, :3]
             e_ref, e_emu = np.abs(r32 - r64).max(), np.abs(v.reshape(r64.shape) - r64).max()
-            print(f'  {k:28s} |ref32-ref64| {e_ref:9.2e}   |emu-ref64| {e_emu:9.2e}   ratio {e_emu / max(e_ref, 1e-12):7.2f}')
+            e_p = np.abs((rp[:, :3] if k == 'cam_pose' else rp) - r32).max() if rp is not None else 0.0
+            print(f'  {k:28s} |ref32-ref64| {e_ref:9.2e}   |pert-ref32| {e_p:9.2e}   |emu-ref64| {e_emu:9.2e}   ratio {e_emu / max(e_ref, e_p, 1e-12):7.2f}')
         for k, v in losses.items():
             r64, r32 = gold[f'loss64/{k}'], gold[f'loss/{k}']
             sc = max(np.abs(r64).max(), 1e-12)

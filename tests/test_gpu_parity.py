@@ -175,13 +175,18 @@ def _make(name, smpl_assets, **spec_over):
 EPS32 = 2.0 ** -24
 
 
-def noise_floor_tol(ref32, ref64, c=4.0, ulps=32):
-    """Tolerance of a k-step comparison against the float64 continuation stored in the fixture: `c` times what the executed
-    float32 reference itself deviates from it (max over the tensor), plus `ulps` float32 roundings of the tensor's magnitude
-    (prefix sums over T frames).  Where the optimisation is well conditioned this is ~1e-6..1e-5, far below the 1e-4
-    north-star bound; where Adam amplifies rounding noise (frames without observations) it is as loose as the reference's
-    own float32 arithmetic is -- and no looser."""
-    return c * float(np.abs(ref32 - ref64).max()) + ulps * EPS32 * max(float(np.abs(ref64).max()), 1.0)
+def noise_floor_tol(ref32, ref64, ref_pert=None, c=4.0, ulps=32):
+    """Tolerance of a k-step comparison against the float64 continuation stored in the fixture: `c` times the larger of the two
+    noise yardsticks the fixture carries, plus `ulps` float32 roundings of the tensor's magnitude (prefix sums over T frames):
+      |ref32 - ref64|    what the executed float32 reference itself deviates from its float64 continuation (rounding INSIDE the loop)
+      |ref_pert - ref32| what ONE float32 rounding of the init state does to the float32 reference (any re-implementation enters
+                         the loop with such differences; Adam's m / sqrt(v) turns a relative gradient change eps into ~lr * k * eps)
+    Where the optimisation is well conditioned this is ~1e-6..1e-5, far below the 1e-4 north-star bound; where Adam amplifies
+    rounding noise (frames without observations) it is as loose as the reference's own float32 arithmetic is -- and no looser."""
+    noise = float(np.abs(ref32 - ref64).max())
+    if ref_pert is not None:
+        noise = max(noise, float(np.abs(ref_pert - ref32).max()))
+    return c * noise + ulps * EPS32 * max(float(np.abs(ref64).max()), 1.0)
 
 
 def _check_init_state(data, gold):
@@ -207,11 +212,11 @@ def _check_trajectory_against_noise_floor(model, data, cfg, gold):
             data['cam_pose_inv'] = G.inverse_transform(data['cam_pose'])
         hist = model.loss_history.cpu().numpy()
         for k in specs['loss_cfg']:
-            r32, r64 = gold[f'loss/{stage}/{k}'], gold[f'loss64/{stage}/{k}']
+            r32, r64, rp = gold[f'loss/{stage}/{k}'], gold[f'loss64/{stage}/{k}'], gold[f'loss_pert/{stage}/{k}']
             got = hist[:n, L.TERM_INDEX[k]]
             # iteration 0 is a pure forward on identical variables
             np.testing.assert_allclose(got[:1], r64[:1], rtol=2e-4, atol=1e-6, err_msg=f'{stage} {k} (iteration 0)')
-            tol = 4.0 * np.abs(r32 - r64).max() + 2e-4 * np.abs(r64).max() + 1e-6
+            tol = 4.0 * max(np.abs(r32 - r64).max(), np.abs(rp - r32).max()) + 2e-4 * np.abs(r64).max() + 1e-6
             err = np.abs(got - r64).max()
             assert err <= tol, f'{stage} {k}: |cuda-ref64| {err:.3e} > {tol:.3e} (|ref32-ref64| {np.abs(r32 - r64).max():.3e})'
     checks = [('cam_pose', data['cam_pose'].cpu().numpy())]
@@ -221,10 +226,10 @@ def _check_trajectory_against_noise_floor(model, data, cfg, gold):
             if k in pd and f'final64/{pid}/{k}' in gold:
                 checks.append((f'{pid}/{k}', pd[k].cpu().numpy()))
     for key, got in checks:
-        r32, r64 = gold[f'final/{key}'], gold[f'final64/{key}']
-        tol = noise_floor_tol(r32, r64, ulps=32 if 'kp_2d_pred' not in key else 256)
+        r32, r64, rp = gold[f'final/{key}'], gold[f'final64/{key}'], gold[f'final_pert/{key}']
+        tol = noise_floor_tol(r32, r64, rp, ulps=32 if 'kp_2d_pred' not in key else 256)
         err = float(np.abs(got.reshape(r64.shape) - r64).max())
-        report[key] = (err, float(np.abs(r32 - r64).max()))
+        report[key] = (err, max(float(np.abs(r32 - r64).max()), float(np.abs(rp - r32).max())))
         assert err <= tol, f'final {key}: |cuda-ref64| {err:.3e} > {tol:.3e} (|ref32-ref64| {np.abs(r32 - r64).max():.3e})'
     return report
 
