@@ -69,7 +69,7 @@ def test_rowop_vjps_match_autograd():
 def _default_lbs_path():
     import os
     e = os.environ.get('GLAMR_LBS_PATH')
-    return (1 if e == 'tc' else 0) if e else 0        # library default (GLAMR_DEFAULT_LBS_TC in csrc/common.cuh)
+    return (1 if e == 'tc' else 0) if e else 1        # library default (GLAMR_DEFAULT_LBS_TC in csrc/common.cuh)
 
 
 @pytest.fixture(params=['tensor_core', 'simt'])
@@ -228,6 +228,14 @@ def _check_trajectory_against_noise_floor(model, data, cfg, gold):
     for key, got in checks:
         r32, r64, rp = gold[f'final/{key}'], gold[f'final64/{key}'], gold[f'final_pert/{key}']
         tol = noise_floor_tol(r32, r64, rp, ulps=32 if 'kp_2d_pred' not in key else 256)
+        # The north star asks for joints / vertices / camera within 1e-4 (metres, radians): the derived bar is never tighter than
+        # that for the OUTPUT poses (a person 5 m from the camera turns 1e-5 rad of its orientation into 5e-5 m of the camera
+        # derived from it, glamr_3dpw), while the optimisation variables themselves keep the derived bar.
+        name_ = key.split('/')[-1]
+        if name_ in ('cam_pose', 'smpl_orient_world', 'root_trans_world'):
+            tol = max(tol, 1e-4)
+        elif name_ == 'kp_2d_pred':
+            tol = max(tol, 2e-2)          # pixels: 1e-4 m at f / z = 1000 / 5
         err = float(np.abs(got.reshape(r64.shape) - r64).max())
         report[key] = (err, max(float(np.abs(r32 - r64).max()), float(np.abs(rp - r32).max())))
         assert err <= tol, f'final {key}: |cuda-ref64| {err:.3e} > {tol:.3e} (|ref32-ref64| {np.abs(r32 - r64).max():.3e})'
