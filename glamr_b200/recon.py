@@ -87,55 +87,66 @@ def rotmats_to_rotvec(mats):
 
     SciPy projects every float32-accurate input onto SO(3) with one SVD per matrix (12 ms for a 300-frame track); the
     same polar factor U V^T is reached here by two Newton steps R <- (R + R^-T) / 2 written with cross products, then
-    the usual largest-diagonal quaternion branch and the rotation-vector scaling (series below 1e-3 rad)."""
-    R0 = R = np.asarray(mats, dtype=np.float64).reshape(-1, 3, 3)
+    the usual largest-diagonal quaternion branch and the rotation-vector scaling (series below 1e-3 rad).  The nine
+    entries are kept as nine contiguous arrays (structure of arrays): every step is a handful of long vector operations."""
+    R0 = np.asarray(mats, dtype=np.float64).reshape(-1, 3, 3)
+    n = R0.shape[0]
+    r = np.ascontiguousarray(R0.reshape(n, 9).T)                      # r[3 i + j] = R[:, i, j], contiguous
+    det = None
     for _ in range(2):
-        a, b, c = R[:, 0], R[:, 1], R[:, 2]                      # rows; cofactor rows are their cross products (explicit:
-        cof = np.empty_like(R)                                   # np.cross is several times slower on [n,3] operands)
-        cof[:, 0, 0] = b[:, 1] * c[:, 2] - b[:, 2] * c[:, 1]
-        cof[:, 0, 1] = b[:, 2] * c[:, 0] - b[:, 0] * c[:, 2]
-        cof[:, 0, 2] = b[:, 0] * c[:, 1] - b[:, 1] * c[:, 0]
-        cof[:, 1, 0] = c[:, 1] * a[:, 2] - c[:, 2] * a[:, 1]
-        cof[:, 1, 1] = c[:, 2] * a[:, 0] - c[:, 0] * a[:, 2]
-        cof[:, 1, 2] = c[:, 0] * a[:, 1] - c[:, 1] * a[:, 0]
-        cof[:, 2, 0] = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
-        cof[:, 2, 1] = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
-        cof[:, 2, 2] = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
-        det = a[:, 0] * cof[:, 0, 0] + a[:, 1] * cof[:, 0, 1] + a[:, 2] * cof[:, 0, 2]
+        a0, a1, a2, b0, b1, b2, c0, c1, c2 = r
+        cof = np.empty_like(r)                                       # cofactor rows = cross products of the other two rows
+        cof[0] = b1 * c2 - b2 * c1
+        cof[1] = b2 * c0 - b0 * c2
+        cof[2] = b0 * c1 - b1 * c0
+        cof[3] = c1 * a2 - c2 * a1
+        cof[4] = c2 * a0 - c0 * a2
+        cof[5] = c0 * a1 - c1 * a0
+        cof[6] = a1 * b2 - a2 * b1
+        cof[7] = a2 * b0 - a0 * b2
+        cof[8] = a0 * b1 - a1 * b0
+        det = a0 * cof[0] + a1 * cof[1] + a2 * cof[2]
         with np.errstate(divide='ignore', invalid='ignore'):
-            R = 0.5 * (R + cof / det[:, None, None])
+            r = 0.5 * (r + cof / det)
     # two Newton steps reach the polar factor only from a near-orthogonal start (HybrIK's float32 matrices).  Rows that are
     # not there yet (or improper / singular inputs) go through SciPy's SVD projection like the reference (which also raises
     # on non-finite input).
-    resid = np.abs(np.einsum('nij,nkj->nik', R, R) - np.eye(3)).reshape(-1, 9).max(axis=1)
-    bad = ~(np.linalg.det(R) > 0) | ~(resid < 1e-9)
+    a0, a1, a2, b0, b1, b2, c0, c1, c2 = r
+    resid = np.maximum.reduce([np.abs(a0 * a0 + a1 * a1 + a2 * a2 - 1), np.abs(b0 * b0 + b1 * b1 + b2 * b2 - 1), np.abs(c0 * c0 + c1 * c1 + c2 * c2 - 1),
+                               np.abs(a0 * b0 + a1 * b1 + a2 * b2), np.abs(a0 * c0 + a1 * c1 + a2 * c2), np.abs(b0 * c0 + b1 * c1 + b2 * c2)])
+    bad = ~(det > 0) | ~(resid < 1e-9)
     if bad.any():
         from scipy.spatial.transform import Rotation
-        R = R.copy()
-        R[bad] = Rotation.from_matrix(R0[bad]).as_matrix()
-    d = np.stack([R[:, 0, 0], R[:, 1, 1], R[:, 2, 2], R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]], axis=1)
-    choice = d.argmax(axis=1)
-    q = np.empty((R.shape[0], 4))
+        r = r.copy()
+        r[:, bad] = Rotation.from_matrix(R0[bad]).as_matrix().reshape(-1, 9).T
+        a0, a1, a2, b0, b1, b2, c0, c1, c2 = r
+    tr = a0 + b1 + c2
+    d = np.stack([a0, b1, c2, tr])
+    choice = d.argmax(axis=0)
+    q = np.empty((4, n))
+    R = r.reshape(3, 3, n)
     for i in range(3):
         sel = np.where(choice == i)[0]
+        if sel.size == 0:
+            continue
         j, k = (i + 1) % 3, (i + 2) % 3
-        q[sel, i] = 1 - d[sel, 3] + 2 * R[sel, i, i]
-        q[sel, j] = R[sel, j, i] + R[sel, i, j]
-        q[sel, k] = R[sel, k, i] + R[sel, i, k]
-        q[sel, 3] = R[sel, k, j] - R[sel, j, k]
+        q[i, sel] = 1 - tr[sel] + 2 * R[i, i, sel]
+        q[j, sel] = R[j, i, sel] + R[i, j, sel]
+        q[k, sel] = R[k, i, sel] + R[i, k, sel]
+        q[3, sel] = R[k, j, sel] - R[j, k, sel]
     sel = np.where(choice == 3)[0]
-    q[sel, 0] = R[sel, 2, 1] - R[sel, 1, 2]
-    q[sel, 1] = R[sel, 0, 2] - R[sel, 2, 0]
-    q[sel, 2] = R[sel, 1, 0] - R[sel, 0, 1]
-    q[sel, 3] = 1 + d[sel, 3]
-    q /= np.linalg.norm(q, axis=1, keepdims=True)
-    q[q[:, 3] < 0] *= -1
-    angle = 2 * np.arctan2(np.linalg.norm(q[:, :3], axis=1), q[:, 3])
+    q[0, sel] = R[2, 1, sel] - R[1, 2, sel]
+    q[1, sel] = R[0, 2, sel] - R[2, 0, sel]
+    q[2, sel] = R[1, 0, sel] - R[0, 1, sel]
+    q[3, sel] = 1 + tr[sel]
+    q /= np.sqrt((q * q).sum(axis=0))
+    q[:, q[3] < 0] *= -1
+    angle = 2 * np.arctan2(np.sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), q[3])
     small = angle <= 1e-3
-    a2 = angle * angle
+    a2_ = angle * angle
     with np.errstate(divide='ignore', invalid='ignore'):
-        scale = np.where(small, 2 + a2 / 12 + 7 * a2 * a2 / 2880, angle / np.sin(angle / 2))
-    return scale[:, None] * q[:, :3]
+        scale = np.where(small, 2 + a2_ / 12 + 7 * a2_ * a2_ / 2880, angle / np.sin(angle / 2))
+    return np.ascontiguousarray((scale * q[:3]).T)
 
 
 def _sec_to_time(secs):
