@@ -439,10 +439,19 @@ def multi_gpu_parity(ctx, cfg, in_dict, iters=20):
         d1 = m1.init_data(copy.deepcopy(in_dict))
         m1.optimize_main(d1, specs['opt_variables'], specs['opt_lr'], iters, specs['loss_cfg'], {'stage': stage})
         diff = {'theta': float((m1._theta - ms._theta).abs().max()), 'cam_pose': float((d1['cam_pose'] - ds['cam_pose']).abs().max())}
-        for k in ['smpl_orient_world', 'root_trans_world', 'kp_2d_pred', 'joints_world']:
-            diff[k] = max(float((a[k] - b[k]).abs().max()) for a, b in zip(d1['person_data'].values(), ds['person_data'].values()))
+        where = {}
+        for k in ['smpl_orient_world', 'root_trans_world', 'kp_2d_pred', 'joints_world', 'smpl_orient_cam_in_world', 'root_trans_cam_in_world']:
+            worst = (-1.0, None)
+            for pid, (a, b) in enumerate(zip(d1['person_data'].values(), ds['person_data'].values())):
+                e = (a[k] - b[k]).abs()
+                m = float(e.max())
+                if m > worst[0]:
+                    pos = [int(i) for i in np.unravel_index(int(e.argmax()), tuple(e.shape))]
+                    worst = (m, {'person': pid, 'index': pos, 'single': float(a[k][tuple(pos)]), 'sharded': float(b[k][tuple(pos)])})
+            diff[k] = worst[0]
+            where[k] = worst[1]
         res = {'max_abs': max(diff['theta'], diff['cam_pose'], diff['smpl_orient_world'], diff['root_trans_world']), 'per_tensor': diff,
-               'iterations': iters, 'bound': 1e-5,
+               'iterations': iters, 'bound': 1e-5, 'where': where,
                'what': f'{ctx.world}-GPU sharded run vs single-GPU run of the same problem, rank 0; kp_2d_pred in pixels'}
         res['ok'] = bool(res['max_abs'] <= res['bound'])
         del m1
