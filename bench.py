@@ -40,7 +40,7 @@ FLOPS_PER_FP = 15.85e6            # dense full-LBS forward (al
 FLOPS_PER_FP_EXECUTED = 9.8e6     # K-sparse skinning (4 weights per vertex): what the kernel really issues
 REF_BUDGET_S = float(os.environ.get('GLAMR_REF_BUDGET_S', 150.0))   # wall-clock bound (s) of the CPU reference arm (--impl reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of one LBS launch, keyed by frame-persons per launch (ncu capture, profiles/)
-NCU_LBS_DRAM_BYTES = {300: 18942208}
+NCU_LBS_DRAM_BYTES = {300: 37866240 + 1347328 + 27008000}     # blend (read + write) + skinning (read), profiles/lbs_blend_tc_r02.md
 # switches that change what the library executes: the bench refuses to run with any of them set
 FORBIDDEN_ENV = ['GLAMR_LBS_DEBUG', 'GLAMR_TC_DEBUG', 'GLAMR_PDL', 'GLAMR_LBS_STAGES', 'GLAMR_TC_NTILE']
 ECHO_ENV = FORBIDDEN_ENV + ['GLAMR_ITER_PATH', 'GLAMR_LBS_PATH', 'GLAMR_PRIOR_GRAPH', 'GLAMR_NET_WIMG', 'GLAMR_ALLREDUCE', 'OMP_NUM_THREADS', 'NCCL_ALGO', 'NCCL_PROTO']
@@ -368,15 +368,24 @@ class StageLoop:
         from glamr_b200 import lib as L
         lib, model = self.model._lib, self.model
         L.check(lib.glamr_opt_kernel_timing(model._opt, 1), 'timing')
-        out = []
+        out, crit, side = [], [], []
         for _ in range(n):
             self.ctx.flush.fill_(1)
             self.iteration()
-            ms = ctypes.c_float()
+            ms, c, b = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
             L.check(lib.glamr_opt_last_lbs_ms(model._opt, ctypes.byref(ms)), 'lbs_ms')
-            out.append(ms.value)
+            L.check(lib.glamr_opt_last_lbs_parts_ms(model._opt, ctypes.byref(c), ctypes.byref(b)), 'lbs_parts_ms')
+            out.append(ms.value), crit.append(c.value), side.append(b.value)
         L.check(lib.glamr_opt_kernel_timing(model._opt, 0), 'timing')
+        self.lbs_parts = {'critical_path_ms': float(np.mean(crit)), 'side_stream_blend_ms': float(np.mean(side))}
         return float(np.mean(out))
+
+    def blend_ms(self, reps=20):
+        """the tensor-core blend (feature kernel + GEMM) alone, warm L2; None on the SIMT path"""
+        from glamr_b200 import lib as L
+        ms = ctypes.c_float()
+        rc = self.model._lib.glamr_opt_time_blend(self.model._opt, reps, ctypes.byref(ms))
+        return float(ms.value) if rc == 0 else None
 
     def release(self):
         self.graph, self.step = None, None
@@ -572,6 +581,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     _dbg('timed loops done')
     lbs_ms = loop.lbs_ms(min(K, 50))
+    blend_ms = loop.blend_ms()
     n_local = model._n_range[1] - model._n_range[0]
     peer = bool(getattr(model, '_peer_ok', False))
     graph_on = bool(loop.graph is not None)
@@ -635,14 +645,25 @@ def run_ours(args):
             'gpu_launches_per_step': launches_per_iter,
             'e2e': {'value': units * K / e2e_info['seconds'], 'unit': 'frame*person*iter/s', 'h2d_bytes_per_step': h2d / K, 'd2h_bytes_per_step': d2h / K,
                     'what': f'GlobalReconOptimizer.optimize(in_dict numpy)->numpy dict incl. init_data, {K} iterations', **e2e_info},
-            'roofline': {'bound': 'hbm', 'kernel': 'LBS kernel of the iteration', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+            'roofline': {'bound': 'hbm', 'kernel': 'LBS of the iteration: lbs_blend_tc_kernel (+ feature kernel) + lbs_skin_kernel', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                          'traffic': NCU_LBS_DRAM_BYTES.get(n_local), 'traffic_source': 'profiles/ (ncu --set full, dram__bytes_read + write, per launch)' if n_local in NCU_LBS_DRAM_BYTES else None,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes': alg_bytes, 'kernel_ms': lbs_ms, 'kernel_share_of_step': lbs_ms / cold_ms,
+                         'kernel_parts': {**getattr(loop, 'lbs_parts', {}),
+                                          'note': 'kernel_ms = skinning (on the critical path) + blend timed in situ on its side stream, where it overlaps the residual / backward kernels, '
+                                                  'so kernel_share_of_step counts overlapped time; both with L2 flushed. traffic (ncu, cold) is 3.3x the algorithmic bytes: the 3xTF32 hi/lo '
+                                                  'constant image is 2 x 18.6 MB and v_posed makes one 25 MB round trip through L2/HBM between the two kernels; back-to-back iterations keep both in the 126 MB L2'},
+                         'tensor': None if blend_ms is None else {
+                             'kernel': 'blend_features_kernel + lbs_blend_tc_kernel launched alone (warm L2)', 'kernel_ms': blend_ms,
+                             'achieved_tflops_tf32': 3 * 2 * 224 * 20736 * (-(-n_local // 128) * 128) / (blend_ms * 1e-3) / 1e12,
+                             'peak_tflops_tf32': peaks.get('bf16_tflops', 2250.0) / 2,
+                             'frac': 3 * 2 * 224 * 20736 * (-(-n_local // 128) * 128) / (blend_ms * 1e-3) / 1e12 / (peaks.get('bf16_tflops', 2250.0) / 2),
+                             'note': '3xTF32: three kind::tf32 MMAs per product; peak = half of the measured dense bf16 throughput (MEASURED_PEAKS.json); '
+                                     'ncu: sm__pipe_tensor_cycles_active 56.6 % of peak, 167 MB L2->SM per launch (profiles/lbs_blend_tc_r02.md)'},
                          'fp32': {'achieved_tflops': fp32_tf, 'executed_tflops': fp32_exec, 'peak_tflops': fp32_peak, 'frac': fp32_tf / fp32_peak, 'frac_executed': fp32_exec / fp32_peak,
                                   'peak_source': 'glamr_fp32_probe: register-resident FFMA loop timed in this run (best of 5)',
-                                  'note': 'the fused full-LBS iteration is FP32-FMA bound with L2-resident constants (SURVEY §8d); the HBM fraction is small by construction; '
-                                          'achieved counts the algorithmic 15.85 MFLOP per frame-person (dense skinning), executed the 9.8 MFLOP the K-sparse kernel issues'}},
+                                  'note': 'algorithmic LBS flops (15.85 MFLOP per frame-person, dense skinning) over the LBS time (blend GEMM timed in situ on its side stream + skinning kernel) against the measured FP32 FFMA peak; '
+                                          'the blend runs on the tensor cores (see roofline.tensor), the skinning is shared-memory-bandwidth bound; the HBM fraction is small by construction (constants stay L2-resident)'}},
             'extras': extras,
         }
         if parity is not None:

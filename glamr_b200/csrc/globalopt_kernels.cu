@@ -755,6 +755,47 @@ extern "C" int glamr_opt_last_lbs_ms(glamr_opt_t* st, float* ms) {
   return GLAMR_OK;
 }
 
+// The two parts of the last timed evaluation separately: the kernel on the iteration's critical path (skinning on the tensor-core
+// path, the whole LBS kernel on the SIMT path) and the blend on its side stream (0 on the SIMT path).
+extern "C" int glamr_opt_last_lbs_parts_ms(glamr_opt_t* st, float* critical_ms, float* blend_ms) {
+  if (!st || !critical_ms || !blend_ms || !st->ev_lbs0) return GLAMR_EINVAL;
+  GLAMR_CUDA_TRY(cudaEventSynchronize(st->ev_lbs1));
+  GLAMR_CUDA_TRY(cudaEventElapsedTime(critical_ms, st->ev_lbs0, st->ev_lbs1));
+  *blend_ms = 0.0f;
+  if (st->vpt_ready && st->aux) {
+    GLAMR_CUDA_TRY(cudaEventSynchronize(st->ev_blend1));
+    GLAMR_CUDA_TRY(cudaEventElapsedTime(blend_ms, st->ev_blend0, st->ev_blend1));
+  }
+  return GLAMR_OK;
+}
+
+// Measurement hook: the blend (features + tensor-core GEMM) of this rank's frame-persons ALONE on its side stream, `reps` launches
+// bracketed by one event pair -> mean ms per launch.  Synchronises.  (In the iteration the blend overlaps other kernels, so its
+// in-situ duration says little about the kernel itself.)
+extern "C" int glamr_opt_time_blend(glamr_opt_t* st, int reps, float* ms) {
+  if (!st || !ms || reps <= 0) return GLAMR_EINVAL;
+  if (lbs_path() != 1 || !st->smpl.tcB || !st->aux) return GLAMR_EUNSUPPORTED;
+  const glamr_problem_t& pb = st->pb;
+  const int nn = pb.n_end - pb.n_begin;
+  if (nn <= 0) return GLAMR_EINVAL;
+  cudaEvent_t e0, e1;
+  GLAMR_CUDA_TRY(cudaEventCreate(&e0));
+  GLAMR_CUDA_TRY(cudaEventCreate(&e1));
+  GLAMR_CUDA_TRY(cudaDeviceSynchronize());
+  GLAMR_CUDA_TRY(cudaEventRecord(e0, st->aux));
+  int rc = GLAMR_OK;
+  for (int i = 0; i < reps && rc == GLAMR_OK; ++i)
+    rc = launch_blend(st->smpl, nn, pb.smpl_pose_all + (size_t)pb.n_begin * 69, pb.smpl_beta_all + (size_t)pb.n_begin * kNB, st->ws, st->aux);
+  cudaEventRecord(e1, st->aux);
+  cudaEventSynchronize(e1);
+  float t = 0.0f;
+  cudaEventElapsedTime(&t, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms = t / reps;
+  return rc;
+}
+
 // timing == 2: durations (ms) between consecutive marks of the last glamr_opt_backward (+ apply) call sequence
 extern "C" int glamr_opt_kernel_times(glamr_opt_t* st, float* ms, int* n) {
   if (!st || !ms || !n || !st->ev_lbs0) return GLAMR_EINVAL;

@@ -103,6 +103,8 @@ def load():
     lib.glamr_opt_reduce_count.restype = ctypes.c_size_t
     lib.glamr_opt_peer_bytes.restype = ctypes.c_size_t
     lib.glamr_fp32_probe.argtypes = [ctypes.c_int, _vp, ctypes.c_size_t, _vp, _vp]
+    lib.glamr_opt_last_lbs_parts_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    lib.glamr_opt_time_blend.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
     lib.glamr_peer_alloc.argtypes = [ctypes.c_size_t, _vp, _vp]
     lib.glamr_peer_open.argtypes = [_vp, _vp]
     lib.glamr_peer_close.argtypes = [_vp]

@@ -246,6 +246,11 @@ int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms
  * the launching stream (do not enable while capturing a CUDA graph); glamr_opt_last_lbs_ms waits for the last pair
  * and returns its duration.  The only entry point that synchronises. */
 int glamr_opt_kernel_timing(glamr_opt_t* st, int enable);
+/* the last timed evaluation split into the critical-path kernel (skinning; whole LBS kernel on the SIMT path) and the side-stream blend */
+int glamr_opt_last_lbs_parts_ms(glamr_opt_t* st, float* critical_ms, float* blend_ms);
+/* mean ms of the blend (feature kernel + tcgen05 GEMM) of this rank's frame-persons launched ALONE `reps` times (synchronises;
+ * GLAMR_EUNSUPPORTED on the SIMT path or before the first evaluation) */
+int glamr_opt_time_blend(glamr_opt_t* st, int reps, float* ms);
 int glamr_opt_last_lbs_ms(glamr_opt_t* st, float* ms);
 /* enable == 2: also record an event after every launch; durations (ms) between consecutive marks of the last
  * backward (+ apply) sequence: memset, traj_fwd, cam_fwd, pose_prep, lbs, joints, residuals, cam_bwd[, scatter], traj_bwd,
