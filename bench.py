@@ -42,7 +42,7 @@ REF_BUDGET_S = float(os.environ.get('GLAMR_REF_BUDGET_S', 150.0))   # wall-clock
 # dram__bytes_read.sum + dram__bytes_write.sum of one LBS launch, keyed by frame-persons per launch (ncu capture, profiles/)
 NCU_LBS_DRAM_BYTES = {300: 37866240 + 1347328 + 27008000}     # blend (read + write) + skinning (read), profiles/lbs_blend_tc_r02.md
 # switches that change what the library executes: the bench refuses to run with any of them set
-FORBIDDEN_ENV = ['GLAMR_LBS_DEBUG', 'GLAMR_TC_DEBUG', 'GLAMR_PDL', 'GLAMR_LBS_STAGES', 'GLAMR_TC_NTILE']
+FORBIDDEN_ENV = ['GLAMR_B200_SO', 'GLAMR_LBS_DEBUG', 'GLAMR_TC_DEBUG', 'GLAMR_PDL', 'GLAMR_LBS_STAGES', 'GLAMR_TC_NTILE']
 ECHO_ENV = FORBIDDEN_ENV + ['GLAMR_ITER_PATH', 'GLAMR_LBS_PATH', 'GLAMR_PRIOR_GRAPH', 'GLAMR_NET_WIMG', 'GLAMR_ALLREDUCE', 'OMP_NUM_THREADS', 'NCCL_ALGO', 'NCCL_PROTO']
 ALL_EXTRAS = ['north_star', 'c4', 'c3', 'c5']
 
@@ -582,6 +582,7 @@ def run_ours(args):
     _dbg('timed loops done')
     lbs_ms = loop.lbs_ms(min(K, 50))
     blend_ms = loop.blend_ms()
+    lbs_parts = dict(getattr(loop, 'lbs_parts', {}))
     n_local = model._n_range[1] - model._n_range[0]
     peer = bool(getattr(model, '_peer_ok', False))
     graph_on = bool(loop.graph is not None)
@@ -645,11 +646,11 @@ def run_ours(args):
             'gpu_launches_per_step': launches_per_iter,
             'e2e': {'value': units * K / e2e_info['seconds'], 'unit': 'frame*person*iter/s', 'h2d_bytes_per_step': h2d / K, 'd2h_bytes_per_step': d2h / K,
                     'what': f'GlobalReconOptimizer.optimize(in_dict numpy)->numpy dict incl. init_data, {K} iterations', **e2e_info},
-            'roofline': {'bound': 'hbm', 'kernel': 'LBS of the iteration: lbs_blend_tc_kernel (+ feature kernel) + lbs_skin_kernel', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+            'roofline': {'bound': 'hbm', 'kernel': 'LBS of the iteration: lbs_blend_tc_kernel (+ feature kernel) + lbs_skin_tc_kernel', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                          'traffic': NCU_LBS_DRAM_BYTES.get(n_local), 'traffic_source': 'profiles/ (ncu --set full, dram__bytes_read + write, per launch)' if n_local in NCU_LBS_DRAM_BYTES else None,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes': alg_bytes, 'kernel_ms': lbs_ms, 'kernel_share_of_step': lbs_ms / cold_ms,
-                         'kernel_parts': {**getattr(loop, 'lbs_parts', {}),
+                         'kernel_parts': {**lbs_parts,
                                           'note': 'kernel_ms = skinning (on the critical path) + blend timed in situ on its side stream, where it overlaps the residual / backward kernels, '
                                                   'so kernel_share_of_step counts overlapped time; both with L2 flushed. traffic (ncu, cold) is 3.3x the algorithmic bytes: the 3xTF32 hi/lo '
                                                   'constant image is 2 x 18.6 MB and v_posed makes one 25 MB round trip through L2/HBM between the two kernels; back-to-back iterations keep both in the 126 MB L2'},

@@ -30,7 +30,7 @@
 // Which implementation runs when the environment does not say otherwise.  A path becomes the default only after its parity
 // tests passed on a B200 (GLAMR_ITER_PATH=fused|legacy, GLAMR_LBS_PATH=tc|simt select explicitly for A/B runs).
 #define GLAMR_DEFAULT_ITER_FUSED 0
-#define GLAMR_DEFAULT_LBS_TC 1        /* verified on B200: 47/48 GPU tests identical to the SIMT path, memcheck clean, 0.113 vs 0.164 ms per iteration */
+#define GLAMR_DEFAULT_LBS_TC 2        /* 2 = tensor-core blend + tensor-core skinning (verified on B200: all GPU tests green, memcheck clean), 1 = tensor-core blend + SIMT skinning, 0 = FP32 SIMT kernel */
 #define GLAMR_DEFAULT_NET_WIMG 0       /* prior-network GEMMs: weight operand as a pre-split image fetched by bulk TMA (GLAMR_NET_WIMG=1) */
 
 namespace glamr {
@@ -58,6 +58,15 @@ constexpr int kTcNTiles = (kV * 3 + kTcN - 1) / kTcN;   // 81
 constexpr int kTcCols = kTcNTiles * kTcN;    // 20736
 constexpr int kTcAStageFloats = 2 * (kTcChunkK / 4) * kTcM * 4;   // hi | lo images of a [128 x 8] K-major core-matrix tile: 2048 floats
 constexpr int kTcBStageFloats = 2 * (kTcChunkK / 4) * kTcN * 4;   // 4096 floats
+// tensor-core skinning (lbs_skin_tc_kernel): T[vertex][frame x 12] = W[vertex][24 joints] . A[24 joints][frame x 12]
+constexpr int kSkF = 20;                     // frames per CTA tile
+constexpr int kSkN = kSkF * 12;              // 240 TMEM columns: the 3x4 blended transform of each frame
+constexpr int kSkKGroups = kNJ / 4;          // 6 groups of 4 joints (K = 24 = 3 MMA steps of 8)
+constexpr int kSkWHalf = kSkKGroups * kVTile * 4;     // 3072 floats: hi (or lo) image of a [128 vertices x 24] K-major tile
+constexpr int kSkWImageFloats = 2 * kSkWHalf;          // 6144 floats = 24,576 B per vertex tile
+constexpr int kSkBHalf = kSkKGroups * kSkN * 4;        // 5760 floats: hi (or lo) image of a [240 x 24] K-major tile
+constexpr int kSkBImageFloats = 2 * kSkBHalf;          // 11520 floats = 46,080 B per 20-frame tile
+constexpr int kSkVpTileFloats = kTileCols * kSkF;      // 7680 floats = 30,720 B: v_posed of 128 vertices x 20 frames
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -347,7 +347,18 @@ GLAMR_HD void quat_angle_dot(const float* a, const float* b, float& angle, float
 }
 
 // Everything of frame-person (p,t) that is not per joint, given the summed joint contributions `kg`.
+// section time stamps of one warp (tools/frame_sections.py): experiment build, device code only
+#if defined(GLAMR_EXPERIMENT) && defined(__CUDACC__)
+__device__ long long g_frame_stamps[2][16];
+#endif
+#if defined(GLAMR_EXPERIMENT) && defined(__CUDA_ARCH__)
+#define GLAMR_STAMP(i) do { if (blockIdx.x == 0 || blockIdx.x == 37) if ((threadIdx.x & 127) == 0) g_frame_stamps[blockIdx.x != 0][i] = clock64(); } while (0)
+#else
+#define GLAMR_STAMP(i) do { } while (0)
+#endif
+
 GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAcc& acc) {
+  GLAMR_STAMP(4);
   const glamr_problem_t& pb = c.pb;
   const glamr_person_t& ps = pb.persons[p];
   const int T = pb.T;
@@ -370,6 +381,7 @@ GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAc
     g_ow[0] += g[0]; g_ow[1] += g[1]; g_ow[2] += g[2];
   }
 
+  GLAMR_STAMP(5);
   // ---- camera-frame pose of the person + cam_traj_rot / cam_traj_trans (global_recon_model.py:512-513, loss_func.py:147-186)
   float Rw[9];
   aa_to_rotmat(ow, Rw);
@@ -451,6 +463,7 @@ GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAc
     }
   }
 
+  GLAMR_STAMP(6);
   float g_Rw[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool any_Rw = false;
   // ---- trajectory smoothness over ALL frames of the person (loss_func.py:117-144)
@@ -522,6 +535,7 @@ GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAc
     }
   }
 
+  GLAMR_STAMP(7);
   // ---- relative transforms between persons (loss_func.py:248-271): W_ij = inv(T_i) T_j against C_ij
   if (pb.rel_target && pb.term_enabled[GLAMR_T_REL_TRANSFORM]) {
     const float gsr = c.gs[GLAMR_T_REL_TRANSFORM];
@@ -592,11 +606,13 @@ GLAMR_HD void frame_rest(const OptCtx& c, int p, int t, const KpGrad& kg, TermAc
       }
     }
   }
+  GLAMR_STAMP(8);
   if (any_Rw) {
     float g[3];
     aa_to_rotmat_vjp(ow, g_Rw, g);
     g_ow[0] += g[0]; g_ow[1] += g[1]; g_ow[2] += g[2];
   }
+  GLAMR_STAMP(9);
 #pragma unroll
   for (int k = 0; k < 3; ++k) { c.sc.g_orient[n * 3 + k] = g_ow[k]; c.sc.g_trans[n * 3 + k] = g_tw[k]; }
 #pragma unroll

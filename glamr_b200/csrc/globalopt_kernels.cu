@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n = blockIdx.x * (kFrameThreads / 32) + wid;
   const int N = c.pb.P * c.pb.T, J = c.pb.J;
+  GLAMR_STAMP(0);
   TermAcc acc;
   acc.clear();
   if (n < N) {
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c
       rodrigues_smplx(c.sc.orient_world + (size_t)n * 3, Rs);
       KpGrad kg;
       kg.clear();
+      GLAMR_STAMP(1);
       for (int k = lane; k < J; k += 32) {
         float v[3], jw[3];
         raw_joint(m, wo, nl, m.joint_map[k], v);
@@ -119,13 +121,16 @@ __global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c
         o[0] = jw[0]; o[1] = jw[1]; o[2] = jw[2];
         kp_joint_terms(c, p, t, k, jw, Rc, tc, Rs, tw, kg);
       }
+      GLAMR_STAMP(2);
 #pragma unroll
       for (int k = 0; k < 3; ++k) { kg.g_tc[k] = warp_sum(kg.g_tc[k]); kg.g_tw[k] = warp_sum(kg.g_tw[k]); }
 #pragma unroll
       for (int k = 0; k < 9; ++k) { kg.g_Rc[k] = warp_sum(kg.g_Rc[k]); kg.g_Rs[k] = warp_sum(kg.g_Rs[k]); }
       kg.kp = warp_sum(kg.kp);
       kg.dist = warp_sum(kg.dist);
+      GLAMR_STAMP(3);
       if (lane == 0) frame_rest(c, p, t, kg, acc);
+      GLAMR_STAMP(10);
     } else if (lane == 0) {
       for (int k = 0; k < 3; ++k) { c.sc.g_orient[(size_t)n * 3 + k] = 0.0f; c.sc.g_trans[(size_t)n * 3 + k] = 0.0f; }
       for (int k = 0; k < 12; ++k) c.sc.g_cam[(size_t)n * 12 + k] = 0.0f;
@@ -139,7 +144,16 @@ __global__ void __launch_bounds__(kFrameThreads) frame_residuals_kernel(OptCtx c
     for (int w = 0; w < kFrameThreads / 32; ++w) s += sm[w * GLAMR_NUM_TERMS + threadIdx.x];
     partial[(size_t)blockIdx.x * GLAMR_NUM_TERMS + threadIdx.x] = s;
   }
+  GLAMR_STAMP(11);
 }
+
+#ifdef GLAMR_EXPERIMENT
+extern "C" int glamr_exp_frame_stamps(long long* out32) {     // experiment build only: the section stamps of two CTAs of the last launch
+  GLAMR_CUDA_TRY(cudaDeviceSynchronize());
+  GLAMR_CUDA_TRY(cudaMemcpyFromSymbol(out32, g_frame_stamps, sizeof(long long) * 32));
+  return GLAMR_OK;
+}
+#endif
 
 __global__ void __launch_bounds__(kFrameThreads) camera_backward_kernel(OptCtx c, double* partial) {
   __shared__ double sm[(kFrameThreads / 32) * GLAMR_NUM_TERMS];
@@ -774,7 +788,7 @@ extern "C" int glamr_opt_last_lbs_parts_ms(glamr_opt_t* st, float* critical_ms, 
 // in-situ duration says little about the kernel itself.)
 extern "C" int glamr_opt_time_blend(glamr_opt_t* st, int reps, float* ms) {
   if (!st || !ms || reps <= 0) return GLAMR_EINVAL;
-  if (lbs_path() != 1 || !st->smpl.tcB || !st->aux) return GLAMR_EUNSUPPORTED;
+  if (lbs_path() < 1 || !st->smpl.tcB || !st->aux) return GLAMR_EUNSUPPORTED;
   const glamr_problem_t& pb = st->pb;
   const int nn = pb.n_end - pb.n_begin;
   if (nn <= 0) return GLAMR_EINVAL;
@@ -875,7 +889,7 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   const int lpad = (pb.T + 31) & ~31;
   const size_t fwd_smem = (size_t)3 * lpad * sizeof(float);
   const bool fused_fwd = st->fused && fwd_smem <= 200 * 1024;
-  const bool tc = lbs_path() == 1 && st->smpl.tcB != nullptr;
+  const bool tc = lbs_path() >= 1 && st->smpl.tcB != nullptr;
   SmplWorkspace wo_pose = wo;
   if (tc) {
     wo_pose.tcA = nullptr;                   // the features belong to blend_features_kernel (side stream); pose prep must not rewrite them

@@ -421,7 +421,10 @@ __global__ void __launch_bounds__(kTcThreads) lbs_blend_tc_kernel(SmplDev m, Smp
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
     const int frame = mtile * kTcM + q * 32 + lane;                              // < w.mpad by construction
-    float* out = w.vpT + (size_t)ntile * kTcN * w.mpad + frame;
+    // v_posed^T [column][frame], or frame-tiled [frame / 20][column][frame % 20] for the tensor-core skinning
+    float* out = w.vp_tiled ? w.vpT + ((size_t)(frame / kSkF) * kTcCols + (size_t)ntile * kTcN) * kSkF + frame % kSkF
+                            : w.vpT + (size_t)ntile * kTcN * w.mpad + frame;
+    const size_t cstride = w.vp_tiled ? (size_t)kSkF : (size_t)w.mpad;
 #pragma unroll 1
     for (int cc = 0; cc < kTcN / 32; ++cc) {
       uint32_t v[32];
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kTcThreads) lbs_blend_tc_kernel(SmplDev m, Smp
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 32; ++j) out[(size_t)(cc * 32 + j) * w.mpad] = __uint_as_float(v[j]);   // 32 lanes = 32 consecutive frames: 128 B per column
+      for (int j = 0; j < 32; ++j) out[(size_t)(cc * 32 + j) * cstride] = __uint_as_float(v[j]);   // 32 lanes = 32 consecutive frames: 128 B per column (2-3 runs when tiled)
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -547,6 +550,130 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_skin_kernel(SmplDev m, int n_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ tensor-core skinning
+// lbs.py:273-284 as a GEMM with a fused epilogue.  The blended transform of vertex v in frame f is T[v][f] = sum_j W[v][j] A_j[f]
+// (12 numbers), i.e. [128 vertices x 24 joints] x [24 joints x (20 frames x 12)] per CTA: M = 128 (TMEM lanes = vertices), N = 240
+// (TMEM columns), K = 24 in three kind::tf32 steps, 3xTF32 (hi*hi + lo*hi + hi*lo) like the blend.  Both operands are pre-tiled
+// UMMA images (W: model constant built at glamr_smpl_create; A: written by pose_prep_frame), so the whole operand traffic of a
+// CTA is three bulk copies: W image 24 KB, A image 45 KB, and the 128 x 20 v_posed block 30 KB (the blend stores v_posed frame-
+// tiled for this).  Epilogue: thread = vertex reads its 12 x 20 transform entries with tcgen05.ld, its v_posed with conflict-free
+// LDS.128 (80-byte row pitch, 240-byte lane stride) and applies T to it -- no shared-memory traffic for the joint transforms,
+// which bounded the SIMT skinning (12 LDS.128 per vertex-frame).  warp 0 = producer, warp 1 = TMEM + MMA, warps 2-5 = epilogue;
+// 101 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM overlap one's epilogue with the other's loads.
+constexpr uint32_t kSkWBytes = kSkWImageFloats * sizeof(float);       // 24,576
+constexpr uint32_t kSkBBytes = kSkBImageFloats * sizeof(float);       // 46,080
+constexpr uint32_t kSkVBytes = kSkVpTileFloats * sizeof(float);       // 30,720
+constexpr size_t kSkinTcSmemBytes = (size_t)kSkWBytes + kSkBBytes + kSkVBytes + 64;
+
+#define GLAMR_TMEM_LD_X16(v, taddr)                                                                                                  \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n" \
+               : "=r"((v)[0]), "=r"((v)[1]), "=r"((v)[2]), "=r"((v)[3]), "=r"((v)[4]), "=r"((v)[5]), "=r"((v)[6]), "=r"((v)[7]),      \
+                 "=r"((v)[8]), "=r"((v)[9]), "=r"((v)[10]), "=r"((v)[11]), "=r"((v)[12]), "=r"((v)[13]), "=r"((v)[14]), "=r"((v)[15])  \
+               : "r"(taddr))
+
+__global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int n, SmplWorkspace w, float* __restrict__ vertices) {
+  extern __shared__ __align__(128) unsigned char sk_raw[];
+  float* Ws = reinterpret_cast<float*>(sk_raw);                       // [hi | lo][6][128][4]
+  float* Bs = Ws + kSkWImageFloats;                                   // [hi | lo][6][240][4]
+  float* Vs = Bs + kSkBImageFloats;                                   // [384 rows = vertex * 3 + coordinate][20 frames]
+  uint64_t* full_ab = reinterpret_cast<uint64_t*>(Vs + kSkVpTileFloats);
+  uint64_t* full_v = full_ab + 1;
+  uint64_t* acc_full = full_ab + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_ab + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int vtile = blockIdx.x, ftile = blockIdx.y;
+  pdl_launch_dependents();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    mbar_init(full_ab, 1);
+    mbar_init(full_v, 1);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(full_ab, kSkWBytes + kSkBBytes);
+      tma_bulk_g2s(Ws, m.skW + (size_t)vtile * kSkWImageFloats, kSkWBytes, full_ab);          // model constant: before the dependency wait
+      pdl_wait();                                                                            // skB (pose prep) and v_posed (blend) below
+      tma_bulk_g2s(Bs, w.skB + (size_t)ftile * kSkBImageFloats, kSkBBytes, full_ab);
+      mbar_expect_tx(full_v, kSkVBytes);
+      tma_bulk_g2s(Vs, w.vpT + ((size_t)ftile * kTcCols + (size_t)vtile * kTileCols) * kSkF, kSkVBytes, full_v);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kSkN >> 3) << 17) | ((uint32_t)(kVTile >> 4) << 24);
+      mbar_wait(full_ab, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < kNJ / 8; ++c) {
+        const float* a = Ws + c * 2 * kVTile * 4;
+        const float* b = Bs + c * 2 * kSkN * 4;
+        const uint64_t dah = umma_desc_kmajor_noswizzle(a, kVTile), dal = umma_desc_kmajor_noswizzle(a + kSkWHalf, kVTile);
+        const uint64_t dbh = umma_desc_kmajor_noswizzle(b, kSkN), dbl = umma_desc_kmajor_noswizzle(b + kSkBHalf, kSkN);
+        umma_tf32(tmem_d, dah, dbh, idesc, c > 0 ? 1u : 0u);
+        umma_tf32(tmem_d, dal, dbh, idesc, 1u);
+        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(acc_full)) : "memory");
+    }
+  } else {
+    // ---- epilogue: warp q = warp % 4 reads TMEM lanes 32 q .. 32 q + 31 (= vertices of this tile)
+    const int q = warp & 3;
+    const int vl = q * 32 + lane;
+    const int gv = vtile * kVTile + vl;
+    const bool v_ok = gv < kV;
+    const int ci = m.compact_of_vertex[min(gv, kVPad - 1)];
+    mbar_wait(full_v, 0);
+    mbar_wait(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const float* vrow = Vs + (size_t)vl * 3 * kSkF;
+#pragma unroll 1
+    for (int g = 0; g < kSkF / 4; ++g) {                         // 4 frames = 48 accumulator columns per step
+      uint32_t t[48];
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 48);
+      GLAMR_TMEM_LD_X16(t, taddr);
+      GLAMR_TMEM_LD_X16(t + 16, taddr + 16);
+      GLAMR_TMEM_LD_X16(t + 32, taddr + 32);
+      const float4 xs = *reinterpret_cast<const float4*>(vrow + g * 4);
+      const float4 ys = *reinterpret_cast<const float4*>(vrow + kSkF + g * 4);
+      const float4 zs = *reinterpret_cast<const float4*>(vrow + 2 * kSkF + g * 4);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const float x[4] = {xs.x, xs.y, xs.z, xs.w}, y[4] = {ys.x, ys.y, ys.z, ys.w}, z[4] = {zs.x, zs.y, zs.z, zs.w};
+#pragma unroll
+      for (int ff = 0; ff < 4; ++ff) {
+        const int fl = ftile * kSkF + g * 4 + ff;                // local frame-person index
+#define GLAMR_T(k) __uint_as_float(t[ff * 12 + (k)])
+        const float ox = fmaf(GLAMR_T(0), x[ff], fmaf(GLAMR_T(1), y[ff], fmaf(GLAMR_T(2), z[ff], GLAMR_T(3))));
+        const float oy = fmaf(GLAMR_T(4), x[ff], fmaf(GLAMR_T(5), y[ff], fmaf(GLAMR_T(6), z[ff], GLAMR_T(7))));
+        const float oz = fmaf(GLAMR_T(8), x[ff], fmaf(GLAMR_T(9), y[ff], fmaf(GLAMR_T(10), z[ff], GLAMR_T(11))));
+#undef GLAMR_T
+        if (fl < n && v_ok) {
+          if (vertices) {
+            float* o = vertices + ((size_t)fl * kV + gv) * 3;
+            o[0] = ox; o[1] = oy; o[2] = oz;
+          }
+          if (ci >= 0) {
+            float* o = w.vcompact + ((size_t)fl * m.S + ci) * 3;
+            o[0] = ox; o[1] = oy; o[2] = oz;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256));
+}
+
 // ------------------------------------------------------------------------------------------------ joints_finalize
 // One warp per frame-person: gather the mapped joints from [24 LBS | picks | extra regressed], re-root at joint 0
 // and apply scale / root translation   (lib/models/smpl.py:299-315)
@@ -625,6 +752,7 @@ static int lbs_set_attrs() {
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
+    GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinTcSmemBytes));
   }
   return GLAMR_OK;
 }
@@ -644,6 +772,11 @@ int launch_skin(const SmplDev& m, int n, const SmplWorkspace& w, float* vertices
   if (n <= 0) return GLAMR_OK;
   int rc;
   if ((rc = lbs_set_attrs())) return rc;
+  if (w.vp_tiled) {
+    lbs_skin_tc_kernel<<<dim3(kNVTiles, (n + kSkF - 1) / kSkF), kTcThreads, kSkinTcSmemBytes, s>>>(m, n, w, vertices);
+    GLAMR_LAUNCH_CHECK();
+    return GLAMR_OK;
+  }
   dim3 grid(kNVTiles, (n + kFramesPerCta - 1) / kFramesPerCta);
   if (m.K == 4) lbs_skin_kernel<4><<<grid, kLbsThreads, kSkinSmemBytes, s>>>(m, 0, n, w, vertices);
   else lbs_skin_kernel<0><<<grid, kLbsThreads, kSkinSmemBytes, s>>>(m, 0, n, w, vertices);
@@ -655,24 +788,37 @@ static int g_lbs_path = -1;
 int lbs_path() {
   if (g_lbs_path < 0) {
     const char* e = getenv("GLAMR_LBS_PATH");
-    g_lbs_path = e ? (strcmp(e, "tc") == 0 ? 1 : 0) : GLAMR_DEFAULT_LBS_TC;
+    g_lbs_path = e ? (strcmp(e, "tc") == 0 ? 2 : strcmp(e, "tcblend") == 0 ? 1 : 0) : GLAMR_DEFAULT_LBS_TC;
   }
   return g_lbs_path;
 }
-int lbs_kernel_count(const SmplDev& m) { return (lbs_path() == 1 && m.tcB) ? 2 : 1; }
+int lbs_kernel_count(const SmplDev& m) { return (lbs_path() >= 1 && m.tcB) ? 2 : 1; }
 
 int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices, cudaStream_t s,
                bool pdl) {
   if (n_end <= n_begin) return GLAMR_OK;
   if (n_begin % kFramesPerCta != 0) return GLAMR_EINVAL;   // the tile-major scratch is indexed by whole frame tiles
   dim3 grid(kNVTiles, (n_end - n_begin + kFramesPerCta - 1) / kFramesPerCta);
-  const int path = lbs_path();             // 1: tensor-core blend GEMM + skinning kernel, 0: the one-kernel FP32 SIMT path
+  const int path = lbs_path();             // >= 1: tensor-core blend GEMM + skinning kernel (2: tensor-core skinning), 0: the one-kernel FP32 SIMT path
   {
     const int rc = lbs_set_attrs();
     if (rc) return rc;
   }
-  if (path == 1 && m.tcB && w.tcA && n_begin == 0) {
+  if (path >= 1 && m.tcB && w.tcA && n_begin == 0) {
     const int mtiles = (n_end + kTcM - 1) / kTcM;
+    if (w.vp_tiled) {
+      const dim3 sgrid(kNVTiles, (n_end + kSkF - 1) / kSkF);
+      if (pdl) {
+        GLAMR_CUDA_TRY(launch_pdl(4, lbs_blend_tc_kernel, dim3(kTcNTiles, mtiles), dim3(kTcThreads), kTcSmemBytes, s, m, w));
+        GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_tc_kernel, sgrid, dim3(kTcThreads), kSkinTcSmemBytes, s, m, n_end, w, vertices));
+      } else {
+        lbs_blend_tc_kernel<<<dim3(kTcNTiles, mtiles), kTcThreads, kTcSmemBytes, s>>>(m, w);
+        GLAMR_LAUNCH_CHECK();
+        lbs_skin_tc_kernel<<<sgrid, kTcThreads, kSkinTcSmemBytes, s>>>(m, n_end, w, vertices);
+        GLAMR_LAUNCH_CHECK();
+      }
+      return GLAMR_OK;
+    }
     if (pdl) {
       GLAMR_CUDA_TRY(launch_pdl(4, lbs_blend_tc_kernel, dim3(kTcNTiles, mtiles), dim3(kTcThreads), kTcSmemBytes, s, m, w));
       if (m.K == 4) GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_kernel<4>, grid, dim3(kLbsThreads), kSkinSmemBytes, s, m, n_begin, n_end, w, vertices));
@@ -814,6 +960,17 @@ extern "C" int glamr_smpl_create(glamr_smpl_t** out, const float* v_template, co
       }
     }
     if ((rc = upload(h, img, &d.tcB))) goto fail;
+    // dense skinning weights W[v][24] as the A operand of the tensor-core skinning: per 128-vertex tile [hi | lo][joint group][vertex][4]
+    std::vector<float> wimg((size_t)kNVTiles * kSkWImageFloats, 0.0f);
+    for (int v = 0; v < kV; ++v)
+      for (int j = 0; j < kNJ; ++j) {
+        const float x = lbs_weights[(size_t)v * kNJ + j];
+        const float hi = tf32_rna(x), lo = tf32_rna(x - hi);
+        float* q = &wimg[(size_t)(v / kVTile) * kSkWImageFloats + ((size_t)(j >> 2) * kVTile + v % kVTile) * 4 + (j & 3)];
+        q[0] = hi;
+        q[kSkWHalf] = lo;
+      }
+    if ((rc = upload(h, wimg, &d.skW))) goto fail;
   }
   {
     std::vector<float> vt((size_t)kVPad * 3, 0.0f), sd((size_t)kVPad * 30, 0.0f);
@@ -901,7 +1058,7 @@ extern "C" int glamr_smpl_destroy(glamr_smpl_t* m) {
 }
 
 extern "C" int glamr_smpl_set_lbs_path(int path) {
-  if (path != 0 && path != 1) return GLAMR_EINVAL;
+  if (path < -1 || path > 2) return GLAMR_EINVAL;     // -1: back to the default (GLAMR_LBS_PATH or the compile-time choice)
   g_lbs_path = path;
   return GLAMR_OK;
 }
@@ -951,7 +1108,9 @@ extern "C" int glamr_smpl_fk24(const glamr_smpl_t* m, int n, const float* global
   if (n == 0) return GLAMR_OK;
   cudaStream_t s = (cudaStream_t)stream;
   SmplWorkspace w = smpl_carve_workspace(workspace, n, m->dev.S);
-  w.tcA = nullptr;                             // FK only: no blend features
+  w.tcA = nullptr;                             // FK only: no blend features, no skinning operands
+  w.skB = nullptr;
+  w.vp_tiled = 0;
   int rc = launch_pose_prep(m->dev, n, global_orient, body_pose, nullptr, 0, w, s);
   if (rc) return rc;
   fk24_finalize_kernel<<<(n * kNJ * 3 + 255) / 256, 256, 0, s>>>(n, w.jposed, root_trans, root_scale, joints);

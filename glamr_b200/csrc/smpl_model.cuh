@@ -12,6 +12,8 @@ struct SmplDev {
   const float* tcB;          // [81 col tiles][28 K chunks][hi | lo][2 K groups][256 cols][4]  the blend basis (posedirs | shapedirs |
                              //                 v_template) pre-split into tf32 hi / lo and pre-tiled as the UMMA K-major core-matrix image:
                              //                 one contiguous 16 KB block per (tile, chunk) = one bulk copy per pipeline stage
+  const float* skW;          // [54 vertex tiles][hi | lo][6 joint groups][128 vertices][4]  dense skinning weights W[v][24], tf32 hi / lo,
+                             //                 UMMA K-major image: one contiguous 24 KB block per vertex tile (lbs_skin_tc_kernel)
   const float* v_template;   // [6912][3]  (padded with zeros)
   const float* shapedirs;    // [6912][30] ([v][c][l] as in the model file)
   const float* j_template;   // [24][3]    J_regressor @ v_template
@@ -45,6 +47,10 @@ struct SmplWorkspace {
   float* vpT;       // [20736][mpad]  blended vertices v_posed, TRANSPOSED (column-major over frames) so that the skinning kernel's
                     //              lanes = frames read 128 contiguous bytes per vertex coordinate
   int mpad;         // frames padded to a multiple of 128
+  float* skB;       // [ceil(mpad/20)][hi | lo][6 joint groups][20 frames x 12][4]  the relative joint transforms as the B operand of the
+                    //              tensor-core skinning (row = frame-in-tile * 12 + element of the 3x4, K = joint), tf32 hi / lo
+  int vp_tiled;     // 1: v_posed is stored frame-tiled for lbs_skin_tc_kernel: [ceil(mpad/20)][20736 cols][20 frames] (the 128 vertices x
+                    //    20 frames of a skinning tile are one contiguous 30,720 B block = one bulk copy); 0: vpT as described above
 };
 
 // FK only (glamr_smpl_fk24): the kinematic-chain scratch without the blend operands (they are carved last)
@@ -56,8 +62,10 @@ inline size_t smpl_workspace_floats(int n, int S) {
   const size_t n32 = ((size_t)n + 31) / 32 * 32;   // the pose feature is tile-major over whole 32-frame tiles
   const size_t n128 = ((size_t)n + kTcM - 1) / kTcM * kTcM;
   return (size_t)n * (kNJ * 3 + (size_t)S * 3 + 3) + n32 * (kPFPad + kNJ * 12) + 64 + 64 +
-         (n128 / kTcM) * kTcChunks * kTcAStageFloats + (size_t)kTcCols * n128;
+         (n128 / kTcM) * kTcChunks * kTcAStageFloats + (size_t)kTcCols * ((n128 + kSkF - 1) / kSkF * kSkF) +
+         ((n128 + kSkF - 1) / kSkF) * kSkBImageFloats + 64;
 }
+int lbs_path();                              // 2 tensor-core blend + tensor-core skinning, 1 tensor-core blend + SIMT skinning, 0 one-kernel FP32 SIMT path
 inline SmplWorkspace smpl_carve_workspace(void* base, int n, int S) {
   SmplWorkspace w;
   float* p = (float*)base;
@@ -69,7 +77,9 @@ inline SmplWorkspace smpl_carve_workspace(void* base, int n, int S) {
   p = (float*)(((uintptr_t)p + 255) & ~(uintptr_t)255);          // bulk-copy sources: 16-byte aligned (256 for good measure)
   w.mpad = (int)(((size_t)n + kTcM - 1) / kTcM * kTcM);
   w.tcA = p; p += (size_t)(w.mpad / kTcM) * kTcChunks * kTcAStageFloats;
-  w.vpT = p;
+  w.skB = p; p += (size_t)((w.mpad + kSkF - 1) / kSkF) * kSkBImageFloats;
+  w.vpT = p;                                   // [20736][mpad] or, frame-tiled, [ceil(mpad/20)][20736][20]
+  w.vp_tiled = lbs_path() == 2 ? 1 : 0;
   return w;
 }
 
@@ -192,6 +202,18 @@ __device__ __forceinline__ void pose_prep_frame(const SmplDev& m, int f, const f
     float4* A = reinterpret_cast<float4*>(w.A + (((size_t)(f >> 5) * kNJ + j) * 32 + (f & 31)) * 12);
 #pragma unroll
     for (int i = 0; i < 3; ++i) A[i] = make_float4(GR[i * 3 + 0], GR[i * 3 + 1], GR[i * 3 + 2], Gt[i] - GJ[i]);
+    if (w.vp_tiled) {
+      // the same 12 numbers as column j of the tensor-core skinning's B operand: row = frame-in-tile * 12 + element
+      float* img = w.skB + (size_t)(f / kSkF) * kSkBImageFloats + ((size_t)(j >> 2) * kSkN + (f % kSkF) * 12) * 4 + (j & 3);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const float v = (i & 3) < 3 ? GR[(i >> 2) * 3 + (i & 3)] : Gt[i >> 2] - GJ[i >> 2];
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        img[i * 4] = hi;
+        img[kSkBHalf + i * 4] = lo;
+      }
+    }
   }
 }
 #endif
@@ -206,7 +228,6 @@ int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, con
 // tensor-core path in two halves (the optimiser pipelines them: the blend depends on body pose / betas only)
 int launch_blend(const SmplDev& m, int n, const float* body_pose, const float* betas, const SmplWorkspace& w, cudaStream_t s);
 int launch_skin(const SmplDev& m, int n, const SmplWorkspace& w, float* vertices, cudaStream_t s);
-int lbs_path();                              // 1 tensor-core blend + skinning kernels, 0 one-kernel FP32 SIMT path
 int lbs_kernel_count(const SmplDev& m);      // kernels one launch_lbs call launches
 int launch_joints_finalize(const SmplDev& m, int n, int orig_joints, const float* root_trans, const float* root_scale,
                            const SmplWorkspace& w, float* joints, cudaStream_t s);

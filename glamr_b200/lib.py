@@ -11,7 +11,11 @@ import subprocess
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, 'libglamr_b200.so')
+# GLAMR_B200_SO: tools/ only -- load another build of the same sources (the -DGLAMR_EXPERIMENT library with the work-skipping switches and
+# section stamps); bench.py refuses to run with it set
+REL_SO_PATH = os.path.join(HERE, 'libglamr_b200.so')
+SO_PATH = os.environ.get('GLAMR_B200_SO') or REL_SO_PATH
+EXP_SO_PATH = os.path.join(HERE, 'libglamr_b200_exp.so')
 CSRC = os.path.join(HERE, 'csrc')
 SOURCES = ['smpl_kernels.cu', 'globalopt_kernels.cu', 'c_api.cu', 'nets_kernels.cu', 'eval_kernels.cu']
 NUM_TERMS = 21
@@ -65,18 +69,27 @@ class GlamrError(RuntimeError):
 _lib = None
 
 
-def nvcc_command(out_path=SO_PATH):
+def nvcc_command(out_path=None, experiment=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     return ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-            '-Xcompiler', '-fPIC', '-shared', '-o', out_path] + srcs
+            '-Xcompiler', '-fPIC', '-shared'] + (['-DGLAMR_EXPERIMENT'] if experiment else []) + \
+           ['-o', out_path or (EXP_SO_PATH if experiment else REL_SO_PATH)] + srcs
+
+
+def build_experiment():
+    """the -DGLAMR_EXPERIMENT variant for tools/ (never loaded by default)"""
+    res = subprocess.run(nvcc_command(experiment=True), capture_output=True, text=True)
+    if res.returncode != 0:
+        raise GlamrError('nvcc failed:\n' + res.stdout + res.stderr)
+    return EXP_SO_PATH
 
 
 def build(force=False, verbose=False):
     """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'glamr_b200.h')]
     newest = max(os.path.getmtime(p) for p in srcs)
-    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= newest:
-        return SO_PATH
+    if not force and os.path.exists(REL_SO_PATH) and os.path.getmtime(REL_SO_PATH) >= newest:
+        return REL_SO_PATH
     cmd = nvcc_command()
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
@@ -85,7 +98,7 @@ def build(force=False, verbose=False):
         raise GlamrError('nvcc failed:\n' + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return SO_PATH
+    return REL_SO_PATH
 
 
 def load():

@@ -67,17 +67,18 @@ def test_rowop_vjps_match_autograd():
 
 # ------------------------------------------------------------------------------------------------ SMPL
 def _default_lbs_path():
-    import os
-    e = os.environ.get('GLAMR_LBS_PATH')
-    return (1 if e == 'tc' else 0) if e else 1        # library default (GLAMR_DEFAULT_LBS_TC in csrc/common.cuh)
+    return -1        # library default: GLAMR_LBS_PATH, else GLAMR_DEFAULT_LBS_TC in csrc/common.cuh
 
 
-@pytest.fixture(params=['tensor_core', 'simt'])
+LBS_PATHS = {'tensor_core': 2, 'tensor_core_blend_simt_skin': 1, 'simt': 0}
+
+
+@pytest.fixture(params=list(LBS_PATHS))
 def lbs_path(request):
-    """both implementations of the blend + skinning: the default tcgen05 3xTF32 blend GEMM + skinning kernel, and the single
-    FP32 SIMT kernel"""
+    """the implementations of the blend + skinning: tcgen05 3xTF32 blend GEMM + tcgen05 skinning, the same blend with the SIMT
+    skinning kernel, and the single FP32 SIMT kernel"""
     from glamr_b200 import lib as L
-    L.check(L.load().glamr_smpl_set_lbs_path(1 if request.param == 'tensor_core' else 0), 'set_lbs_path')
+    L.check(L.load().glamr_smpl_set_lbs_path(LBS_PATHS[request.param]), 'set_lbs_path')
     yield request.param
     L.check(L.load().glamr_smpl_set_lbs_path(_default_lbs_path()), 'set_lbs_path')
 
@@ -137,14 +138,15 @@ def test_smpl_tensor_core_and_simt_paths_agree(smpl_assets):
     o, p = torch.randn(n, 3, generator=gen).to(DEV), (torch.randn(n, 69, generator=gen) * 0.4).to(DEV)
     b, t = torch.randn(n, 10, generator=gen).to(DEV), torch.randn(n, 3, generator=gen).to(DEV)
     outs = []
-    for path in (1, 0):
+    for path in (2, 1, 0):
         L.check(L.load().glamr_smpl_set_lbs_path(path), 'set_lbs_path')
         r = smpl(global_orient=o, body_pose=p, betas=b, root_trans=t)
         outs.append((r.joints.clone(), r.vertices.clone()))
     L.check(L.load().glamr_smpl_set_lbs_path(_default_lbs_path()), 'set_lbs_path')
-    dj, dv = (outs[0][0] - outs[1][0]).abs().max().item(), (outs[0][1] - outs[1][1]).abs().max().item()
-    print(f'tensor-core vs SIMT: joints {dj:.2e}, vertices {dv:.2e}')
-    assert dj < 5e-6 and dv < 5e-6
+    for name, k in (('tensor-core blend + skinning', 0), ('tensor-core blend + SIMT skinning', 1)):
+        dj, dv = (outs[k][0] - outs[2][0]).abs().max().item(), (outs[k][1] - outs[2][1]).abs().max().item()
+        print(f'{name} vs SIMT: joints {dj:.2e}, vertices {dv:.2e}')
+        assert dj < 5e-6 and dv < 5e-6
 
 
 def test_smpl_dense_skinning_model(smpl_assets, lbs_path):

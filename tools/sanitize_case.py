@@ -24,12 +24,13 @@ a = make_smpl_assets(0)
 smpl = SMPL(a, device=dev)
 g = torch.Generator().manual_seed(0)
 n = 33
-for path in (1, 0):
+for path in (2, 1, 0):
     L.check(L.load().glamr_smpl_set_lbs_path(path), 'path')
     out = smpl(global_orient=torch.randn(n, 3, generator=g).to(dev), body_pose=(torch.randn(n, 69, generator=g) * 0.3).to(dev),
                betas=torch.randn(n, 10, generator=g).to(dev), root_trans=torch.randn(n, 3, generator=g).to(dev))
     torch.cuda.synchronize()
     print('smpl path', path, float(out.vertices.abs().sum()))
+L.check(L.load().glamr_smpl_set_lbs_path(-1), 'path')        # back to the default for the optimiser runs below
 prior = MotionTrajJointModel(None, dev, None, smpl=smpl, states=make_prior_states(1234))
 which = os.environ.get('CASES', 'glamr_dynamic,glamr_static_multi,glamr_3dpw').split(',')
 for cfg_id in which:
