@@ -43,7 +43,7 @@ REF_BUDGET_S = float(os.environ.get('GLAMR_REF_BUDGET_S', 150.0))   # wall-clock
 NCU_LBS_DRAM_BYTES = {300: 37866240 + 1347328 + 27008000}     # blend (read + write) + skinning (read), profiles/lbs_blend_tc_r02.md
 # switches that change what the library executes: the bench refuses to run with any of them set
 FORBIDDEN_ENV = ['GLAMR_B200_SO', 'GLAMR_LBS_DEBUG', 'GLAMR_TC_DEBUG', 'GLAMR_PDL', 'GLAMR_LBS_STAGES', 'GLAMR_TC_NTILE']
-ECHO_ENV = FORBIDDEN_ENV + ['GLAMR_ITER_PATH', 'GLAMR_LBS_PATH', 'GLAMR_PRIOR_GRAPH', 'GLAMR_NET_WIMG', 'GLAMR_ALLREDUCE', 'OMP_NUM_THREADS', 'NCCL_ALGO', 'NCCL_PROTO']
+ECHO_ENV = FORBIDDEN_ENV + ['GLAMR_ITER_PATH', 'GLAMR_LBS_PATH', 'GLAMR_PRIOR_GRAPH', 'GLAMR_NET_WIMG', 'GLAMR_NET_SKINNY', 'GLAMR_ALLREDUCE', 'OMP_NUM_THREADS', 'NCCL_ALGO', 'NCCL_PROTO']
 ALL_EXTRAS = ['north_star', 'c4', 'c3', 'c5']
 
 

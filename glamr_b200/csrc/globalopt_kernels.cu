@@ -916,6 +916,12 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   }
   GLAMR_MARK();
   bool forked = false;
+#ifdef GLAMR_EXPERIMENT
+  // experiment build only (tools/iter_skip_exp.py): GLAMR_EXP_SKIP bit 1 = no pipelined blend, 2 = no skinning, 4 = no residual kernel, 8 = no backward kernel
+  static const int exp_skip = getenv("GLAMR_EXP_SKIP") ? atoi(getenv("GLAMR_EXP_SKIP")) : 0;
+#else
+  constexpr int exp_skip = 0;
+#endif
   if (n_end > n_begin) {
     const int nn = n_end - n_begin;
     const float* pose_l = pb.smpl_pose_all + (size_t)n_begin * 69;
@@ -930,13 +936,15 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
         st->vpt_ready = 1;
       }
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
-      if ((rc = launch_skin(st->smpl, nn, wo, nullptr, s))) return rc;
+      if (!(exp_skip & 2))
+        if ((rc = launch_skin(st->smpl, nn, wo, nullptr, s))) return rc;
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
       // the blend of the next evaluation: side stream, concurrent with the residual / backward kernels below
       GLAMR_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
       GLAMR_CUDA_TRY(cudaStreamWaitEvent(st->aux, st->ev_fork, 0));
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend0, st->aux));
-      if ((rc = launch_blend(st->smpl, nn, pose_l, beta_l, wo, st->aux))) return rc;
+      if (!(exp_skip & 1))
+        if ((rc = launch_blend(st->smpl, nn, pose_l, beta_l, wo, st->aux))) return rc;
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend1, st->aux));
       GLAMR_CUDA_TRY(cudaEventRecord(st->ev_join, st->aux));
       forked = true;
@@ -963,7 +971,8 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   double* part_res = st->partial;
   double* part_traj = st->partial + (size_t)st->slots_res * GLAMR_NUM_TERMS;
   double* part_cam3 = part_traj + (size_t)(pb.P + st->cam_blocks) * GLAMR_NUM_TERMS;
-  GLAMR_CUDA_TRY(launch_pdl(8, frame_residuals_kernel, dim3(st->slots_res), dim3(kFrameThreads), 0, s, c, st->smpl, wo, n_begin, part_res));
+  if (!(exp_skip & 4))
+    GLAMR_CUDA_TRY(launch_pdl(8, frame_residuals_kernel, dim3(st->slots_res), dim3(kFrameThreads), 0, s, c, st->smpl, wo, n_begin, part_res));
   GLAMR_MARK();
   if (from_persons) {
     GLAMR_CUDA_TRY(launch_pdl(16, camera_backward_kernel, dim3(st->slots_cam), dim3(kFrameThreads), 0, s, c, part_cam3));
@@ -971,8 +980,9 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
     GLAMR_MARK();
   }
   const int n_slots = st->slots_res + pb.P + st->cam_blocks + (from_persons ? st->slots_cam : 0);
-  GLAMR_CUDA_TRY(launch_pdl(16, traj_cam_backward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1, part_traj,
-                            (const double*)st->partial, n_slots, reduce_buf, st->tickets, pc));
+  if (!(exp_skip & 8))
+    GLAMR_CUDA_TRY(launch_pdl(16, traj_cam_backward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1, part_traj,
+                              (const double*)st->partial, n_slots, reduce_buf, st->tickets, pc));
   GLAMR_MARK();
   if (forked) GLAMR_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join, 0));      // the side stream rejoins before the evaluation ends
   return GLAMR_OK;

@@ -418,8 +418,100 @@ static int gemm_tc_launch(cudaStream_t s, int M, int N, int K, const float* X, i
   return GLAMR_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ skinny GEMM (M <= 256)
+// The prior runs at batch 1-4: its linear layers are [50 B x K] x [K x N] with K, N <= 512 -- a few MFLOP each, ~450 of them
+// in dependent order per sequence, so the figure of merit is the LATENCY of one launch, not its throughput.  One warp owns an
+// 8 x 4 output tile and splits K across its lanes: every lane issues all its 16-byte loads of the 8 X rows and 4 W rows at once
+// (no shared memory, no block barrier, one global round trip), accumulates 32 partial dot products in FP32 and the warp folds
+// them with a 31-shuffle transpose-reduction that leaves output (r, c) on lane 4 r + c.  ~2 us per launch against ~12 us for the
+// one-tile tcgen05 kernel at M = 50 (profiles/init_breakdown_r02d_p1.txt), exact FP32 FMA arithmetic.
+constexpr int kSkinnyMaxM = 256;
+template <int ACT, bool VEC>
+__global__ void __launch_bounds__(128) gemm_skinny_kernel(int M, int N, int K, const float* __restrict__ X, int ldx, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, const float* __restrict__ bias2, float* __restrict__ Y, int ldy) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int m0 = blockIdx.y * 8, n0 = (blockIdx.x * 4 + wid) * 4;
+  if (n0 >= N) return;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+  const float* xr[8];
+  const float* wr[4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) xr[r] = X + (size_t)min(m0 + r, M - 1) * ldx;      // rows / columns past the edge are clamped, never stored
+#pragma unroll
+  for (int c = 0; c < 4; ++c) wr[c] = W + (size_t)min(n0 + c, N - 1) * K;
+  if (VEC) {
+#pragma unroll 2
+    for (int k = 4 * lane; k < K; k += 128) {
+      float4 xv[8], wv[4];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) xv[r] = *reinterpret_cast<const float4*>(xr[r] + k);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(wr[c] + k);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          acc[r * 4 + c] = fmaf(xv[r].w, wv[c].w, fmaf(xv[r].z, wv[c].z, fmaf(xv[r].y, wv[c].y, fmaf(xv[r].x, wv[c].x, acc[r * 4 + c]))));
+    }
+  } else {
+#pragma unroll 4
+    for (int k = lane; k < K; k += 32) {
+      float xv[8], wv[4];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) xv[r] = xr[r][k];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wv[c] = wr[c][k];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r * 4 + c] = fmaf(xv[r], wv[c], acc[r * 4 + c]);
+    }
+  }
+  // transpose-reduce: after the step with offset o a lane keeps the half of its values whose index has bit o equal to its own lane bit
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float keep = up ? acc[i + o] : acc[i];
+      const float send = up ? acc[i] : acc[i + o];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  const int m = m0 + (lane >> 2), n = n0 + (lane & 3);
+  if (m < M && n < N) {
+    float v = acc[0] + (bias ? bias[n] : 0.0f) + (bias2 ? bias2[n] : 0.0f);
+    if (ACT == 1) v = fmaxf(v, 0.0f);
+    Y[(size_t)m * ldy + n] = v;
+  }
+}
+
+static int gemm_skinny_launch(cudaStream_t s, int M, int N, int K, const float* X, int ldx, const float* W, const float* b, const float* b2,
+                              float* Y, int ldy, int act) {
+  const dim3 grid((N + 15) / 16, (M + 7) / 8);
+  const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)X | (uintptr_t)W) % 16 == 0);
+  if (vec) {
+    if (act == 1) gemm_skinny_kernel<1, true><<<grid, 128, 0, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+    else gemm_skinny_kernel<0, true><<<grid, 128, 0, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+  } else {
+    if (act == 1) gemm_skinny_kernel<1, false><<<grid, 128, 0, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+    else gemm_skinny_kernel<0, false><<<grid, 128, 0, s>>>(M, N, K, X, ldx, W, b, b2, Y, ldy);
+  }
+  GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+
+static int g_skinny = -1;       // GLAMR_NET_SKINNY=0 sends the small problems to the tile kernels again (A/B runs)
 static int gemm(cudaStream_t s, int M, int N, int K, const float* X, int ldx, const float* W, const float* b, const float* b2, float* Y,
                 int ldy, int act) {
+  if (g_skinny < 0) {
+    const char* e = getenv("GLAMR_NET_SKINNY");
+    g_skinny = e ? atoi(e) : 1;
+  }
+  if (g_skinny && M <= kSkinnyMaxM) return gemm_skinny_launch(s, M, N, K, X, ldx, W, b, b2, Y, ldy, act);
   if (g_gemm_mode == 1) {
     static int ntile = -1;     // GLAMR_TC_NTILE = 32 | 128 forces one tile shape (experiments); default: by problem height
     if (ntile < 0) {
@@ -472,6 +564,9 @@ __global__ void __launch_bounds__(128) add_layernorm_kernel(int M, const float* 
 
 // ------------------------------------------------------------------------------------------------ attention, head dim 32
 // Q rows (tq * B + b), K/V rows (tk * B + b); row strides ldq / ldkv; 8 heads of 32.  key_mask [B,Sk] (1 = ignore) or NULL.
+// grid (B, 8 heads, ceil(Sq / 8)): a CTA stages the head's K / V once and its 4 warps take 2 queries each, so that the kernel is
+// one short dependent chain deep at the batch sizes of the inference (B = 1-4) instead of Sq / 4 of them.
+constexpr int kAttnQChunk = 8;
 __global__ void __launch_bounds__(128) attention_kernel(int B, int Sq, int Sk, const float* __restrict__ Q, int ldq,
                                                         const float* __restrict__ K, const float* __restrict__ V, int ldkv,
                                                         const uint8_t* __restrict__ key_mask, float* __restrict__ O, int ldo) {
@@ -487,7 +582,8 @@ __global__ void __launch_bounds__(128) attention_kernel(int B, int Sq, int Sk, c
   }
   __syncthreads();
   const float scale = 0.17677669529663687f;   // 1/sqrt(32)
-  for (int q = w; q < Sq; q += 4) {
+  const int q_end = min(Sq, ((int)blockIdx.z + 1) * kAttnQChunk);
+  for (int q = blockIdx.z * kAttnQChunk + w; q < q_end; q += 4) {
     const float qd = Q[((size_t)q * B + b) * ldq + h * 32 + lane] * scale;   // torch scales q before q k^T
     float sc[2];
 #pragma unroll
@@ -508,7 +604,7 @@ __global__ void __launch_bounds__(128) attention_kernel(int B, int Sq, int Sk, c
     Ps[w][lane + 32] = e1 / den;
     __syncwarp();
     float o = 0.0f;
-    for (int j = 0; j < Sk; ++j) o = fmaf(Ps[w][j], Vs[j][lane], o);
+    for (int j = 0; j < Sk; ++j) o = fmaf(Ps[w][j], Vs[j][lane], o);      // in key order (the reference's softmax(QK^T) V row sum)
     O[((size_t)q * B + b) * ldo + h * 32 + lane] = o;
     __syncwarp();
   }
@@ -721,7 +817,7 @@ int mha(cudaStream_t s, Arena& A, const AttnW& w, int B, int Sq, int Sk, const f
   int rc;
   if ((rc = gemm(s, Mq, 256, 256, q_src, 256, w.in_w, w.in_b, nullptr, q, 256, 0))) return rc;
   if ((rc = gemm(s, Mk, 512, 256, kv_src, 256, w.in_w + 256 * 256, w.in_b + 256, nullptr, kv, 512, 0))) return rc;
-  attention_kernel<<<dim3(B, 8), 128, 0, s>>>(B, Sq, Sk, q, 256, kv, kv + 256, 512, mask, att, 256);
+  attention_kernel<<<dim3(B, 8, (Sq + kAttnQChunk - 1) / kAttnQChunk), 128, 0, s>>>(B, Sq, Sk, q, 256, kv, kv + 256, 512, mask, att, 256);
   GLAMR_LAUNCH_CHECK();
   if ((rc = gemm(s, Mq, 256, 256, att, 256, w.out_w, w.out_b, nullptr, out, 256, 0))) return rc;
   A.used = mark;
@@ -883,6 +979,62 @@ extern "C" int glamr_infiller_window_forward(const glamr_net* n, int B, const fl
   if ((rc = gemm(s, Mc, 69, 256, h2, 256, ofw, ofb, nullptr, dec_out, 69, 0))) return rc;
   concat_time_kernel<<<64, 256, 0, s>>>(10, Sc, B, 69, in_pose, dec_out, out_pose);
   GLAMR_LAUNCH_CHECK();
+  return GLAMR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ all windows of a sequence
+// motion_infiller_vae.py:618-632: the autoregressive sweep of 50-frame windows with stride 30.  Window i reads frames
+// [30 i, 30 i + 50) of the running pose (zeros past the end), masks keys that are invisible or past the end (the 10 past frames
+// are always usable), and its first min(40, T - 30 i) output frames replace the running pose.  One call for the whole sweep: the
+// window staging / commit are two small kernels instead of a dozen framework ops per window.
+__global__ void window_prep_kernel(int T, int B, int s0, const float* __restrict__ pose, const uint8_t* __restrict__ key_pad_all,
+                                   float* __restrict__ win, uint8_t* __restrict__ kp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = B * 69;
+  if (i < 50 * row) {
+    const int t = i / row;
+    win[i] = (s0 + t < T) ? pose[(size_t)(s0 + t) * row + (i - t * row)] : 0.0f;
+  }
+  if (i < B * 50) {
+    const int b = i / 50, t = i - b * 50;
+    kp[i] = t < 10 ? 0 : ((s0 + t < T) ? key_pad_all[(size_t)b * T + s0 + t] : 1);
+  }
+}
+__global__ void window_commit_kernel(int B, int s0, int nfr, const float* __restrict__ out, float* __restrict__ pose) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = B * 69;
+  if (i < nfr * row) pose[(size_t)s0 * row + i] = out[i];
+}
+
+extern "C" size_t glamr_infiller_sequence_workspace_floats(int B) {
+  return glamr_infiller_workspace_floats(B) + (size_t)90 * B * 69 + (size_t)(B * 50 + 3) / 4 + 192;
+}
+
+//   pose_io [T,B,69]: the input body pose, overwritten with the infilled pose   key_pad_all [B,T] uint8 (1 = frame invisible)
+//   eps [n_windows][eps_rows][128] with eps_rows in {1, B}, n_windows = ceil((T - 10) / 30)
+extern "C" int glamr_infiller_forward(const glamr_net* n, int T, int B, float* pose_io, const uint8_t* key_pad_all, const float* eps,
+                                      int eps_rows, float* workspace, size_t workspace_floats, void* stream) {
+  if (!n || T <= 10 || B <= 0 || !pose_io || !key_pad_all || !eps || !workspace || (eps_rows != 1 && eps_rows != B)) return GLAMR_EINVAL;
+  if (workspace_floats < glamr_infiller_sequence_workspace_floats(B)) return GLAMR_ENOSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* win = workspace;
+  float* out = win + (size_t)50 * B * 69;
+  uint8_t* kp = reinterpret_cast<uint8_t*>(out + (size_t)40 * B * 69);
+  float* rest = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(kp + (size_t)B * 50) + 255) & ~(uintptr_t)255);
+  const size_t rest_floats = workspace_floats - (size_t)(rest - workspace);
+  const int nwin = (T - 10 + 29) / 30;
+  const int prep_blocks = (50 * B * 69 + 255) / 256;
+  for (int i = 0; i < nwin; ++i) {
+    const int s0 = i * 30;
+    window_prep_kernel<<<prep_blocks, 256, 0, s>>>(T, B, s0, pose_io, key_pad_all, win, kp);
+    GLAMR_LAUNCH_CHECK();
+    const int rc = glamr_infiller_window_forward(n, B, win, kp, eps + (size_t)i * eps_rows * 128, eps_rows, out, rest, rest_floats, stream);
+    if (rc) return rc;
+    const int nfr = (s0 + 40 < T ? s0 + 40 : T) - s0;
+    window_commit_kernel<<<(nfr * B * 69 + 255) / 256, 256, 0, s>>>(B, s0, nfr, out, pose_io);
+    GLAMR_LAUNCH_CHECK();
+  }
   return GLAMR_OK;
 }
 

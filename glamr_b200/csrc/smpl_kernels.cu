@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_skin_kernel(SmplDev m, int n_
 constexpr uint32_t kSkWBytes = kSkWImageFloats * sizeof(float);       // 24,576
 constexpr uint32_t kSkBBytes = kSkBImageFloats * sizeof(float);       // 46,080
 constexpr uint32_t kSkVBytes = kSkVpTileFloats * sizeof(float);       // 30,720
-constexpr size_t kSkinTcSmemBytes = (size_t)kSkWBytes + kSkBBytes + kSkVBytes + 64;
+constexpr size_t kSkinTcSmemBytes = (size_t)kSkWBytes + kSkBBytes + kSkVBytes + 128;
 
 #define GLAMR_TMEM_LD_X16(v, taddr)                                                                                                  \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n" \
@@ -572,26 +572,38 @@ constexpr size_t kSkinTcSmemBytes = (size_t)kSkWBytes + kSkBBytes + kSkVBytes + 
                  "=r"((v)[8]), "=r"((v)[9]), "=r"((v)[10]), "=r"((v)[11]), "=r"((v)[12]), "=r"((v)[13]), "=r"((v)[14]), "=r"((v)[15])  \
                : "r"(taddr))
 
+constexpr int kSkTilesPerCta = 3;       // frame tiles one CTA sweeps (W stays in shared memory; 54 x 5 CTAs = one wave at 300 frames)
+
 __global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int n, SmplWorkspace w, float* __restrict__ vertices) {
   extern __shared__ __align__(128) unsigned char sk_raw[];
   float* Ws = reinterpret_cast<float*>(sk_raw);                       // [hi | lo][6][128][4]
   float* Bs = Ws + kSkWImageFloats;                                   // [hi | lo][6][240][4]
   float* Vs = Bs + kSkBImageFloats;                                   // [384 rows = vertex * 3 + coordinate][20 frames]
-  uint64_t* full_ab = reinterpret_cast<uint64_t*>(Vs + kSkVpTileFloats);
-  uint64_t* full_v = full_ab + 1;
-  uint64_t* acc_full = full_ab + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_ab + 3);
+  uint64_t* full_w = reinterpret_cast<uint64_t*>(Vs + kSkVpTileFloats);
+  uint64_t* full_b = full_w + 1;          // A image of the current frame tile has landed
+  uint64_t* full_v = full_w + 2;          // v_posed block has landed
+  uint64_t* acc_full = full_w + 3;        // the tile's MMAs have completed (accumulator readable)
+  uint64_t* b_empty = full_w + 4;         // ... and no longer read Bs: the next A image may be fetched
+  uint64_t* v_empty = full_w + 5;         // the 4 epilogue warps are done with Vs
+  uint64_t* acc_empty = full_w + 6;       // ... and with the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_w + 7);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int vtile = blockIdx.x, ftile = blockIdx.y;
+  const int vtile = blockIdx.x;
+  const int ftile0 = blockIdx.y * kSkTilesPerCta;
+  const int ntiles = min(kSkTilesPerCta, (n + kSkF - 1) / kSkF - ftile0);
   pdl_launch_dependents();
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 0) {
-    mbar_init(full_ab, 1);
+    mbar_init(full_w, 1);
+    mbar_init(full_b, 1);
     mbar_init(full_v, 1);
     mbar_init(acc_full, 1);
+    mbar_init(b_empty, 1);
+    mbar_init(v_empty, 4);
+    mbar_init(acc_empty, 4);
     mbar_fence_init();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -601,29 +613,41 @@ __global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int 
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(full_ab, kSkWBytes + kSkBBytes);
-      tma_bulk_g2s(Ws, m.skW + (size_t)vtile * kSkWImageFloats, kSkWBytes, full_ab);          // model constant: before the dependency wait
-      pdl_wait();                                                                            // skB (pose prep) and v_posed (blend) below
-      tma_bulk_g2s(Bs, w.skB + (size_t)ftile * kSkBImageFloats, kSkBBytes, full_ab);
-      mbar_expect_tx(full_v, kSkVBytes);
-      tma_bulk_g2s(Vs, w.vpT + ((size_t)ftile * kTcCols + (size_t)vtile * kTileCols) * kSkF, kSkVBytes, full_v);
+      mbar_expect_tx(full_w, kSkWBytes);
+      tma_bulk_g2s(Ws, m.skW + (size_t)vtile * kSkWImageFloats, kSkWBytes, full_w);          // model constant: before the dependency wait
+      pdl_wait();                                                                           // skB (pose prep) and v_posed (blend) below
+      for (int it = 0; it < ntiles; ++it) {
+        const int ftile = ftile0 + it;
+        if (it > 0) mbar_wait(b_empty, (it - 1) & 1);
+        mbar_expect_tx(full_b, kSkBBytes);
+        tma_bulk_g2s(Bs, w.skB + (size_t)ftile * kSkBImageFloats, kSkBBytes, full_b);
+        if (it > 0) mbar_wait(v_empty, (it - 1) & 1);
+        mbar_expect_tx(full_v, kSkVBytes);
+        tma_bulk_g2s(Vs, w.vpT + ((size_t)ftile * kTcCols + (size_t)vtile * kTileCols) * kSkF, kSkVBytes, full_v);
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kSkN >> 3) << 17) | ((uint32_t)(kVTile >> 4) << 24);
-      mbar_wait(full_ab, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      mbar_wait(full_w, 0);
+      for (int it = 0; it < ntiles; ++it) {
+        mbar_wait(full_b, it & 1);
+        if (it > 0) mbar_wait(acc_empty, (it - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int c = 0; c < kNJ / 8; ++c) {
-        const float* a = Ws + c * 2 * kVTile * 4;
-        const float* b = Bs + c * 2 * kSkN * 4;
-        const uint64_t dah = umma_desc_kmajor_noswizzle(a, kVTile), dal = umma_desc_kmajor_noswizzle(a + kSkWHalf, kVTile);
-        const uint64_t dbh = umma_desc_kmajor_noswizzle(b, kSkN), dbl = umma_desc_kmajor_noswizzle(b + kSkBHalf, kSkN);
-        umma_tf32(tmem_d, dah, dbh, idesc, c > 0 ? 1u : 0u);
-        umma_tf32(tmem_d, dal, dbh, idesc, 1u);
-        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+        for (int c = 0; c < kNJ / 8; ++c) {
+          const float* a = Ws + c * 2 * kVTile * 4;
+          const float* b = Bs + c * 2 * kSkN * 4;
+          const uint64_t dah = umma_desc_kmajor_noswizzle(a, kVTile), dal = umma_desc_kmajor_noswizzle(a + kSkWHalf, kVTile);
+          const uint64_t dbh = umma_desc_kmajor_noswizzle(b, kSkN), dbl = umma_desc_kmajor_noswizzle(b + kSkBHalf, kSkN);
+          umma_tf32(tmem_d, dah, dbh, idesc, c > 0 ? 1u : 0u);
+          umma_tf32(tmem_d, dal, dbh, idesc, 1u);
+          umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+        }
+        // both arrive once every MMA issued so far has completed
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b_empty)) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(acc_full)) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(acc_full)) : "memory");
     }
   } else {
     // ---- epilogue: warp q = warp % 4 reads TMEM lanes 32 q .. 32 q + 31 (= vertices of this tile)
@@ -632,40 +656,50 @@ __global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int 
     const int gv = vtile * kVTile + vl;
     const bool v_ok = gv < kV;
     const int ci = m.compact_of_vertex[min(gv, kVPad - 1)];
-    mbar_wait(full_v, 0);
-    mbar_wait(acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float* vrow = Vs + (size_t)vl * 3 * kSkF;
+    for (int it = 0; it < ntiles; ++it) {
+      const int ftile = ftile0 + it;
+      mbar_wait(full_v, it & 1);
+      mbar_wait(acc_full, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-    for (int g = 0; g < kSkF / 4; ++g) {                         // 4 frames = 48 accumulator columns per step
-      uint32_t t[48];
-      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 48);
-      GLAMR_TMEM_LD_X16(t, taddr);
-      GLAMR_TMEM_LD_X16(t + 16, taddr + 16);
-      GLAMR_TMEM_LD_X16(t + 32, taddr + 32);
-      const float4 xs = *reinterpret_cast<const float4*>(vrow + g * 4);
-      const float4 ys = *reinterpret_cast<const float4*>(vrow + kSkF + g * 4);
-      const float4 zs = *reinterpret_cast<const float4*>(vrow + 2 * kSkF + g * 4);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const float x[4] = {xs.x, xs.y, xs.z, xs.w}, y[4] = {ys.x, ys.y, ys.z, ys.w}, z[4] = {zs.x, zs.y, zs.z, zs.w};
+      for (int g = 0; g < kSkF / 4; ++g) {                         // 4 frames = 48 accumulator columns per step
+        uint32_t t[48];
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 48);
+        GLAMR_TMEM_LD_X16(t, taddr);
+        GLAMR_TMEM_LD_X16(t + 16, taddr + 16);
+        GLAMR_TMEM_LD_X16(t + 32, taddr + 32);
+        const float4 xs = *reinterpret_cast<const float4*>(vrow + g * 4);
+        const float4 ys = *reinterpret_cast<const float4*>(vrow + kSkF + g * 4);
+        const float4 zs = *reinterpret_cast<const float4*>(vrow + 2 * kSkF + g * 4);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float x[4] = {xs.x, xs.y, xs.z, xs.w}, y[4] = {ys.x, ys.y, ys.z, ys.w}, z[4] = {zs.x, zs.y, zs.z, zs.w};
 #pragma unroll
-      for (int ff = 0; ff < 4; ++ff) {
-        const int fl = ftile * kSkF + g * 4 + ff;                // local frame-person index
+        for (int ff = 0; ff < 4; ++ff) {
+          const int fl = ftile * kSkF + g * 4 + ff;                // local frame-person index
 #define GLAMR_T(k) __uint_as_float(t[ff * 12 + (k)])
-        const float ox = fmaf(GLAMR_T(0), x[ff], fmaf(GLAMR_T(1), y[ff], fmaf(GLAMR_T(2), z[ff], GLAMR_T(3))));
-        const float oy = fmaf(GLAMR_T(4), x[ff], fmaf(GLAMR_T(5), y[ff], fmaf(GLAMR_T(6), z[ff], GLAMR_T(7))));
-        const float oz = fmaf(GLAMR_T(8), x[ff], fmaf(GLAMR_T(9), y[ff], fmaf(GLAMR_T(10), z[ff], GLAMR_T(11))));
+          const float ox = fmaf(GLAMR_T(0), x[ff], fmaf(GLAMR_T(1), y[ff], fmaf(GLAMR_T(2), z[ff], GLAMR_T(3))));
+          const float oy = fmaf(GLAMR_T(4), x[ff], fmaf(GLAMR_T(5), y[ff], fmaf(GLAMR_T(6), z[ff], GLAMR_T(7))));
+          const float oz = fmaf(GLAMR_T(8), x[ff], fmaf(GLAMR_T(9), y[ff], fmaf(GLAMR_T(10), z[ff], GLAMR_T(11))));
 #undef GLAMR_T
-        if (fl < n && v_ok) {
-          if (vertices) {
-            float* o = vertices + ((size_t)fl * kV + gv) * 3;
-            o[0] = ox; o[1] = oy; o[2] = oz;
-          }
-          if (ci >= 0) {
-            float* o = w.vcompact + ((size_t)fl * m.S + ci) * 3;
-            o[0] = ox; o[1] = oy; o[2] = oz;
+          if (fl < n && v_ok) {
+            if (vertices) {
+              float* o = vertices + ((size_t)fl * kV + gv) * 3;
+              o[0] = ox; o[1] = oy; o[2] = oz;
+            }
+            if (ci >= 0) {
+              float* o = w.vcompact + ((size_t)fl * m.S + ci) * 3;
+              o[0] = ox; o[1] = oy; o[2] = oz;
+            }
           }
         }
+      }
+      // release the accumulator and the v_posed block for the next frame tile
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc_empty);
+        mbar_arrive(v_empty);
       }
     }
   }
@@ -773,7 +807,7 @@ int launch_skin(const SmplDev& m, int n, const SmplWorkspace& w, float* vertices
   int rc;
   if ((rc = lbs_set_attrs())) return rc;
   if (w.vp_tiled) {
-    lbs_skin_tc_kernel<<<dim3(kNVTiles, (n + kSkF - 1) / kSkF), kTcThreads, kSkinTcSmemBytes, s>>>(m, n, w, vertices);
+    lbs_skin_tc_kernel<<<dim3(kNVTiles, ((n + kSkF - 1) / kSkF + kSkTilesPerCta - 1) / kSkTilesPerCta), kTcThreads, kSkinTcSmemBytes, s>>>(m, n, w, vertices);
     GLAMR_LAUNCH_CHECK();
     return GLAMR_OK;
   }
@@ -807,7 +841,7 @@ int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, con
   if (path >= 1 && m.tcB && w.tcA && n_begin == 0) {
     const int mtiles = (n_end + kTcM - 1) / kTcM;
     if (w.vp_tiled) {
-      const dim3 sgrid(kNVTiles, (n_end + kSkF - 1) / kSkF);
+      const dim3 sgrid(kNVTiles, ((n_end + kSkF - 1) / kSkF + kSkTilesPerCta - 1) / kSkTilesPerCta);
       if (pdl) {
         GLAMR_CUDA_TRY(launch_pdl(4, lbs_blend_tc_kernel, dim3(kTcNTiles, mtiles), dim3(kTcThreads), kTcSmemBytes, s, m, w));
         GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_tc_kernel, sgrid, dim3(kTcThreads), kSkinTcSmemBytes, s, m, n_end, w, vertices));

@@ -2,10 +2,9 @@
 ``MotionTrajJointModel`` (motion_infiller/models/motion_traj_joint_model.py:17-145): ``inference(batch, sample_num)``,
 ``get_motion_latent``, ``get_traj_latent``.
 
-The networks run in ``glamr_infiller_window_forward`` / ``glamr_trajpred_forward`` (glamr_b200/csrc/nets_kernels.cu);
-this module only slices the 50-frame windows (autoregressive over windows exactly like
-MotionInfillerVAE.inference_multi_step, motion_infiller_vae.py:618-632, but batched over ALL sequences instead of the
-reference's batch of one), runs SMPL FK for the joint-position features and reshapes the outputs into the reference's
+The networks run in ``glamr_infiller_forward`` (the autoregressive sweep of 50-frame windows of
+MotionInfillerVAE.inference_multi_step, motion_infiller_vae.py:618-632, batched over ALL sequences instead of the
+reference's batch of one) and ``glamr_trajpred_forward`` (glamr_b200/csrc/nets_kernels.cu); this module runs SMPL FK for the joint-position features and reshapes the outputs into the reference's
 dict layout.  Weights come from the reference's Lightning checkpoints (state_dict names are kept) or from an explicit
 state dict; there is no CPU fallback.
 """
@@ -27,6 +26,9 @@ def _declare(lib):
     if getattr(lib, '_nets_declared', False):
         return
     lib.glamr_infiller_workspace_floats.restype = ctypes.c_size_t
+    lib.glamr_infiller_sequence_workspace_floats.restype = ctypes.c_size_t
+    lib.glamr_infiller_forward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                                                                     ctypes.c_void_p]
     lib.glamr_trajpred_workspace_floats.restype = ctypes.c_size_t
     lib.glamr_net_set_tensor.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
     lib.glamr_infiller_window_forward.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p,
@@ -131,7 +133,7 @@ class MotionInfillerVAE:
         latent = batch.get('in_motion_latent')
         latent = None if latent is None else latent.to(dev, torch.float32).contiguous()
         B0, T = pose_in.shape[:2]
-        self.net.workspace(self.net.lib.glamr_infiller_workspace_floats(B0 * sample_num))        # sized before any capture
+        self.net.workspace(self.net.lib.glamr_infiller_sequence_workspace_floats(B0 * sample_num))        # sized before any capture
         key = ('infill', B0, T, sample_num, None if latent is None else tuple(latent.shape))
         with torch.cuda.device(dev):
             body = self.graphs.run(key, lambda a, b, c: self._windows(a, b, c, sample_num), (pose_in, frame_mask, latent))
@@ -142,39 +144,27 @@ class MotionInfillerVAE:
         return data
 
     def _windows(self, pose_in, frame_mask, latent, sample_num):
-        """motion_infiller_vae.py:618-632: autoregressive 50-frame windows (device tensors in, [B0, S, T, 69] out; no host sync)"""
+        """motion_infiller_vae.py:618-632: autoregressive 50-frame windows, stride 30 -- one library call for the whole sweep
+        (device tensors in, [B0, S, T, 69] out; no host sync)"""
         dev = self.device
         B0, T = pose_in.shape[:2]
-        pose = pose_in.repeat_interleave(sample_num, dim=0).transpose(0, 1).contiguous().clone()       # [T,B,69]
-        key_pad_all = ~(frame_mask == 1)
-        key_pad_all = key_pad_all.repeat_interleave(sample_num, dim=0)
         B = B0 * sample_num
-        lib = self.net.lib
-        ws = self.net.workspace(lib.glamr_infiller_workspace_floats(B))
-        out = torch.empty((PAST + CUR, B, 69), dtype=torch.float32, device=dev)
-        pieces = []
+        pose = pose_in.repeat_interleave(sample_num, dim=0).transpose(0, 1).contiguous().clone()       # [T,B,69], overwritten in place
+        key_pad_all = (~(frame_mask == 1)).repeat_interleave(sample_num, dim=0).to(torch.uint8).contiguous()      # [B,T]
         nwin = int(np.ceil((T - PAST) / CUR))
-        for i in range(nwin):
-            s, e = i * CUR, i * CUR + WINDOW
-            eb = min(e, T)
-            win = torch.zeros((WINDOW, B, 69), dtype=torch.float32, device=dev)
-            win[:eb - s] = pose[s:eb]
-            kp = torch.ones((B, WINDOW), dtype=torch.uint8, device=dev)
-            kp[:, :eb - s] = key_pad_all[:, s:eb].to(torch.uint8)
-            kp[:, :PAST] = 0
-            if latent is not None and latent.dim() == 3:                 # [B, windows, nz]: one latent per sequence
-                eps, rows = latent[:, i].repeat_interleave(sample_num, dim=0).contiguous(), B
-            elif latent is not None:
-                eps, rows = latent[[i]].contiguous(), 1
-            else:
-                eps, rows = torch.randn((B, NZ), device=dev), B
-            L.check(lib.glamr_infiller_window_forward(self.net.h, B, win.data_ptr(), kp.data_ptr(), eps.data_ptr(), rows, out.data_ptr(),
-                                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
-                    'glamr_infiller_window_forward')
-            nfr = min(e - FUT, T) - s
-            pose[s:s + nfr] = out[:nfr]
-            pieces.append(out[:nfr].clone() if i == 0 else out[PAST:nfr].clone())
-        return torch.cat(pieces, dim=0).transpose(0, 1).reshape(B0, sample_num, T, 69).contiguous()
+        if latent is not None and latent.dim() == 3:                 # [B0, windows, nz]: one latent per sequence and window
+            eps, rows = latent[:, :nwin].repeat_interleave(sample_num, dim=0).transpose(0, 1).contiguous(), B
+        elif latent is not None:                                     # [windows, nz]: shared by the batch
+            eps, rows = latent[:nwin].contiguous(), 1
+        else:
+            eps, rows = torch.randn((nwin, B, NZ), device=dev), B
+        if eps.shape[0] < nwin:
+            raise ValueError(f'{nwin} windows need {nwin} latents, got {eps.shape[0]}')
+        lib = self.net.lib
+        ws = self.net.workspace(lib.glamr_infiller_sequence_workspace_floats(B))
+        L.check(lib.glamr_infiller_forward(self.net.h, T, B, pose.data_ptr(), key_pad_all.data_ptr(), eps.data_ptr(), rows, ws.data_ptr(), ws.numel(),
+                                           torch.cuda.current_stream().cuda_stream), 'glamr_infiller_forward')
+        return pose.transpose(0, 1).reshape(B0, sample_num, T, 69).contiguous()
 
 
 class TrajPredVAE:

@@ -120,6 +120,12 @@ size_t glamr_trajpred_workspace_floats(int T, int B);
 int glamr_infiller_window_forward(const glamr_net_t* n, int B, const float* in_pose, const uint8_t* key_pad_mask,
                                   const float* eps, int eps_rows, float* out_pose, float* workspace, size_t workspace_floats,
                                   void* stream);
+/* The whole autoregressive sweep of motion_infiller_vae.py:618-632 (windows of 50 frames, stride 30) in one call:
+ *   pose_io [T,B,69]: input body pose, overwritten with the infilled pose   key_pad_all [B,T] uint8 (1 = frame invisible)
+ *   eps [ceil((T-10)/30)][eps_rows][128], eps_rows in {1,B}   workspace >= glamr_infiller_sequence_workspace_floats(B) floats */
+size_t glamr_infiller_sequence_workspace_floats(int B);
+int glamr_infiller_forward(const glamr_net_t* n, int T, int B, float* pose_io, const uint8_t* key_pad_all, const float* eps,
+                           int eps_rows, float* workspace, size_t workspace_floats, void* stream);
 /*   in_joint_pos [T,B,69] (23 joints from SMPL.get_joints)   eps as above   init_xy [B,2] / init_heading [B] or NULL
  *   out_local_traj [T,B,11]   out_trans [T,B,3]   out_orient_aa [T,B,3] */
 int glamr_trajpred_forward(const glamr_net_t* n, int T, int B, const float* in_joint_pos, const float* eps, int eps_rows,

@@ -409,6 +409,28 @@ def test_product_fails_loudly_on_cpu_device(smpl_assets):
 
 
 # ------------------------------------------------------------------------------------------------ learned prior
+@pytest.mark.parametrize('M,N,K,relu', [(1, 512, 256, 1), (2, 256, 512, 0), (50, 256, 69, 0), (50, 768, 256, 0), (30, 69, 256, 0), (64, 11, 256, 0),
+                                        (7, 5, 3, 1), (200, 512, 384, 1), (256, 256, 512, 0), (257, 256, 256, 0), (1500, 512, 384, 1),
+                                        (3200, 768, 256, 0)])
+def test_linear_layer_kernels_match_float64(M, N, K, relu):
+    """Y = act(X W^T + b) of the prior networks: the skinny FP32 kernel (M <= 256), the tcgen05 3xTF32 tile kernel and the
+    FP32 tile kernel (mode 0) against a float64 product; ragged M / N / K, unaligned K (69) included"""
+    import ctypes
+    from glamr_b200 import lib as L
+    lib = L.load()
+    lib.glamr_linear_forward.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    g = torch.Generator().manual_seed(M * 1000 + N)
+    X, W, b = torch.randn(M, K, generator=g).to(DEV), (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV), torch.randn(N, generator=g).to(DEV)
+    ref = X.double() @ W.double().T + b.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    for mode in (1, 0):
+        Y = torch.full((M, N), float('nan'), device=DEV)
+        L.check(lib.glamr_linear_forward(M, N, K, X.data_ptr(), W.data_ptr(), b.data_ptr(), relu, Y.data_ptr(), mode, torch.cuda.current_stream().cuda_stream), 'linear')
+        err = float((Y.double() - ref).abs().max())
+        assert err < 2e-5, f'mode {mode}: {err}'       # |x w| ~ 1 per output: 3xTF32 keeps ~2e-6, FP32 FMA ~1e-6
+
+
 @pytest.fixture(scope='module')
 def cuda_prior(smpl_assets):
     from glamr_b200.motion_traj import MotionTrajJointModel
