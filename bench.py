@@ -40,7 +40,7 @@ FLOPS_PER_FP = 15.85e6            # dense full-LBS forward (al
 FLOPS_PER_FP_EXECUTED = 9.8e6     # K-sparse skinning (4 weights per vertex): what the kernel really issues
 REF_BUDGET_S = float(os.environ.get('GLAMR_REF_BUDGET_S', 150.0))   # wall-clock bound (s) of the CPU reference arm (--impl reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of one LBS launch, keyed by frame-persons per launch (ncu capture, profiles/)
-NCU_LBS_DRAM_BYTES = {300: 37866240 + 1347328 + 27008000}     # blend (read + write) + skinning (read), profiles/lbs_blend_tc_r02.md
+NCU_LBS_DRAM_BYTES = {300: 37885952 + 3018752 + 26944768}     # blend (read + write) + tensor-core skinning (read), profiles/lbs_skin_tc_r02.md
 # switches that change what the library executes: the bench refuses to run with any of them set
 FORBIDDEN_ENV = ['GLAMR_B200_SO', 'GLAMR_LBS_DEBUG', 'GLAMR_TC_DEBUG', 'GLAMR_PDL', 'GLAMR_LBS_STAGES', 'GLAMR_TC_NTILE']
 ECHO_ENV = FORBIDDEN_ENV + ['GLAMR_ITER_PATH', 'GLAMR_LBS_PATH', 'GLAMR_PRIOR_GRAPH', 'GLAMR_NET_WIMG', 'GLAMR_NET_SKINNY', 'GLAMR_ALLREDUCE', 'OMP_NUM_THREADS', 'NCCL_ALGO', 'NCCL_PROTO']
@@ -651,7 +651,7 @@ def run_ours(args):
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes': alg_bytes, 'kernel_ms': lbs_ms, 'kernel_share_of_step': lbs_ms / cold_ms,
                          'kernel_parts': {**lbs_parts,
-                                          'note': 'kernel_ms = skinning (on the critical path) + blend timed in situ on its side stream, where it overlaps the residual / backward kernels, '
+                                          'note': 'kernel_ms = skinning (on the critical path) + blend timed in situ on its side stream, where it overlaps the other kernels of the evaluation, '
                                                   'so kernel_share_of_step counts overlapped time; both with L2 flushed. traffic (ncu, cold) is 3.3x the algorithmic bytes: the 3xTF32 hi/lo '
                                                   'constant image is 2 x 18.6 MB and v_posed makes one 25 MB round trip through L2/HBM between the two kernels; back-to-back iterations keep both in the 126 MB L2'},
                          'tensor': None if blend_ms is None else {
@@ -664,7 +664,7 @@ def run_ours(args):
                          'fp32': {'achieved_tflops': fp32_tf, 'executed_tflops': fp32_exec, 'peak_tflops': fp32_peak, 'frac': fp32_tf / fp32_peak, 'frac_executed': fp32_exec / fp32_peak,
                                   'peak_source': 'glamr_fp32_probe: register-resident FFMA loop timed in this run (best of 5)',
                                   'note': 'algorithmic LBS flops (15.85 MFLOP per frame-person, dense skinning) over the LBS time (blend GEMM timed in situ on its side stream + skinning kernel) against the measured FP32 FFMA peak; '
-                                          'the blend runs on the tensor cores (see roofline.tensor), the skinning is shared-memory-bandwidth bound; the HBM fraction is small by construction (constants stay L2-resident)'}},
+                                          'both LBS kernels run on the tensor cores now (3xTF32: roofline.tensor is the blend; the skinning is a K = 24 GEMM whose time is its TMEM epilogue and operand loads), so this FP32-FMA fraction is a comparison figure against the round-1 SIMT kernel, not a bound; the HBM fraction is small by construction (constants stay L2-resident)'}},
             'extras': extras,
         }
         if parity is not None:

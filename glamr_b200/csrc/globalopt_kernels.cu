@@ -659,6 +659,7 @@ struct glamr_opt {
   cudaStream_t aux;
   cudaEvent_t ev_fork, ev_join;
   int vpt_ready;
+  int blend_early;            // the pipelined blend is launched at the top of the evaluation into the other v_posed buffer
   cudaEvent_t ev[24];         // timing == 2: one event after every launch of glamr_opt_backward / glamr_opt_apply
   int n_ev;
   // glamr_opt_iterate: one captured iteration (backward + apply), valid for the arguments it was captured with
@@ -714,6 +715,16 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
                o_gt = take(3 * N), o_gcam = take(12 * N), o_gcf = take(12 * T), o_gxy = take(2 * N), o_gh = take(N),
                o_m = take(pb->n_params), o_v = take(pb->n_params);
   const size_t o_ws = take(smpl_workspace_floats((int)N, smpl->dev.S));
+  {
+    const char* ep = getenv("GLAMR_ITER_PATH");
+    st->fused = ep ? (strcmp(ep, "fused") == 0) : GLAMR_DEFAULT_ITER_FUSED;
+    // GLAMR_BLEND_EARLY=0|1: launch the pipelined blend after the skinning (0) or at the top of the evaluation (1, needs the
+    // second v_posed buffer); the fused iteration advances the step count inside its tail kernel and keeps the single buffer
+    const char* e = getenv("GLAMR_BLEND_EARLY");
+    st->blend_early = (e ? atoi(e) != 0 : GLAMR_DEFAULT_BLEND_EARLY != 0) && !st->fused;
+  }
+  const size_t n128 = (N + kTcM - 1) / kTcM * kTcM;
+  const size_t o_vp2 = st->blend_early ? take((size_t)kTcCols * ((n128 + kSkF - 1) / kSkF * kSkF)) : 0;        // second v_posed buffer (pipelined blend)
   st->arena_bytes = floats * sizeof(float);
   cudaError_t e = cudaMalloc(&st->arena, st->arena_bytes);
   if (e != cudaSuccess) { free(st); return (int)e; }
@@ -724,10 +735,6 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   st->adam.beta_pow = (double*)(b + o_beta);
   st->tickets = (unsigned int*)(b + o_ticket);
   st->kpg = (KpGrad*)(b + o_kpg);
-  {
-    const char* e = getenv("GLAMR_ITER_PATH");
-    st->fused = e ? (strcmp(e, "fused") == 0) : GLAMR_DEFAULT_ITER_FUSED;
-  }
   st->sc.heading = b + o_heading; st->sc.xy = b + o_xy; st->sc.traj_local = b + o_tl; st->sc.orient_base = b + o_ob;
   st->sc.trans_base = b + o_tb; st->sc.orient_world = b + o_ow; st->sc.trans_world = b + o_tw; st->sc.cam = b + o_cam;
   st->sc.cam_inv = b + o_caminv; st->sc.cam_d6 = b + o_camd6; st->sc.joints_world = b + o_jw; st->sc.kp_pred = b + o_kp;
@@ -736,6 +743,10 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   st->sc.grad = nullptr;
   st->adam.m = b + o_m; st->adam.v = b + o_v;
   st->ws = smpl_carve_workspace(b + o_ws, (int)N, smpl->dev.S);
+  if (st->blend_early) {
+    st->ws.vpT2 = b + o_vp2;
+    st->ws.flip_src = st->adam.beta_pow + 2;
+  }
   const double one[3] = {1.0, 1.0, 0.0};
   e = cudaMemcpy(st->adam.beta_pow, one, sizeof(one), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(st->arena); free(st); return (int)e; }
@@ -899,6 +910,55 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
       GLAMR_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming));
     }
   }
+  {
+    static bool carve = false;
+    if (!carve && (smem_carveout_mask() & 4)) {
+      carve = true;
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(traj_cam_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(cam_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(frame_residuals_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(camera_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(camera_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(traj_cam_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+  }
+  bool forked = false;
+#ifdef GLAMR_EXPERIMENT
+  // experiment build only (tools/iter_skip_exp.py): GLAMR_EXP_SKIP bit 1 = no pipelined blend, 2 = no skinning, 4 = no residual kernel, 8 = no backward kernel
+  static const int exp_skip = getenv("GLAMR_EXP_SKIP") ? atoi(getenv("GLAMR_EXP_SKIP")) : 0;
+#else
+  constexpr int exp_skip = 0;
+#endif
+  const float* const pose_l = pb.smpl_pose_all + (size_t)n_begin * 69;
+  const float* const beta_l = pb.smpl_beta_all + (size_t)n_begin * kNB;
+  // the blend of the NEXT evaluation (it depends on body pose / betas only): side stream, concurrent with this evaluation
+  auto fork_blend = [&]() -> int {
+    SmplWorkspace wn = wo;
+    wn.flip_add = 1;                           // with two buffers: the one the next step's skinning will read
+    GLAMR_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
+    GLAMR_CUDA_TRY(cudaStreamWaitEvent(st->aux, st->ev_fork, 0));
+    if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend0, st->aux));
+    if (!(exp_skip & 1)) {
+      const int rc = launch_blend(st->smpl, n_end - n_begin, pose_l, beta_l, wn, st->aux);
+      if (rc) return rc;
+    }
+    if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend1, st->aux));
+    GLAMR_CUDA_TRY(cudaEventRecord(st->ev_join, st->aux));
+    forked = true;
+    return GLAMR_OK;
+  };
+  if (tc && n_end > n_begin) {
+    if (!st->vpt_ready) {                 // first evaluation after create / a new sequence: the current buffer is filled in order
+      const int rc = launch_blend(st->smpl, n_end - n_begin, pose_l, beta_l, wo, s);
+      if (rc) return rc;
+      st->vpt_ready = 1;
+    }
+    if (st->blend_early) {
+      const int rc = fork_blend();
+      if (rc) return rc;
+    }
+  }
   if (fused_fwd) {
     if (fwd_smem > 48 * 1024 && st->fwd_smem_set < fwd_smem) {
       GLAMR_CUDA_TRY(cudaFuncSetAttribute(forward_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
@@ -915,39 +975,19 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
     GLAMR_CUDA_TRY(launch_pdl(1, cam_forward_kernel, dim3(st->slots_cam), dim3(kFrameThreads), 0, s, c));
   }
   GLAMR_MARK();
-  bool forked = false;
-#ifdef GLAMR_EXPERIMENT
-  // experiment build only (tools/iter_skip_exp.py): GLAMR_EXP_SKIP bit 1 = no pipelined blend, 2 = no skinning, 4 = no residual kernel, 8 = no backward kernel
-  static const int exp_skip = getenv("GLAMR_EXP_SKIP") ? atoi(getenv("GLAMR_EXP_SKIP")) : 0;
-#else
-  constexpr int exp_skip = 0;
-#endif
   if (n_end > n_begin) {
     const int nn = n_end - n_begin;
-    const float* pose_l = pb.smpl_pose_all + (size_t)n_begin * 69;
-    const float* beta_l = pb.smpl_beta_all + (size_t)n_begin * kNB;
     int rc;
     if (!fused_fwd)
       if ((rc = launch_pose_prep(st->smpl, nn, st->sc.orient_world + (size_t)n_begin * 3, pose_l, beta_l, 1, wo_pose, s, true))) return rc;
     GLAMR_MARK();
     if (tc) {
-      if (!st->vpt_ready) {                 // first evaluation after create / a new sequence: prime the pipeline in order
-        if ((rc = launch_blend(st->smpl, nn, pose_l, beta_l, wo, s))) return rc;
-        st->vpt_ready = 1;
-      }
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
       if (!(exp_skip & 2))
         if ((rc = launch_skin(st->smpl, nn, wo, nullptr, s))) return rc;
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
-      // the blend of the next evaluation: side stream, concurrent with the residual / backward kernels below
-      GLAMR_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
-      GLAMR_CUDA_TRY(cudaStreamWaitEvent(st->aux, st->ev_fork, 0));
-      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend0, st->aux));
-      if (!(exp_skip & 1))
-        if ((rc = launch_blend(st->smpl, nn, pose_l, beta_l, wo, st->aux))) return rc;
-      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend1, st->aux));
-      GLAMR_CUDA_TRY(cudaEventRecord(st->ev_join, st->aux));
-      forked = true;
+      if (!st->blend_early)                 // single buffer: the next blend may only start once this skinning has read v_posed
+        if ((rc = fork_blend())) return rc;
     } else {
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
       if ((rc = launch_lbs(st->smpl, 0, nn, beta_l, wo, nullptr, s, true))) return rc;

@@ -422,8 +422,9 @@ __global__ void __launch_bounds__(kTcThreads) lbs_blend_tc_kernel(SmplDev m, Smp
     const int q = warp & 3;
     const int frame = mtile * kTcM + q * 32 + lane;                              // < w.mpad by construction
     // v_posed^T [column][frame], or frame-tiled [frame / 20][column][frame % 20] for the tensor-core skinning
-    float* out = w.vp_tiled ? w.vpT + ((size_t)(frame / kSkF) * kTcCols + (size_t)ntile * kTcN) * kSkF + frame % kSkF
-                            : w.vpT + (size_t)ntile * kTcN * w.mpad + frame;
+    float* const vpb = vp_buffer(w);
+    float* out = w.vp_tiled ? vpb + ((size_t)(frame / kSkF) * kTcCols + (size_t)ntile * kTcN) * kSkF + frame % kSkF
+                            : vpb + (size_t)ntile * kTcN * w.mpad + frame;
     const size_t cstride = w.vp_tiled ? (size_t)kSkF : (size_t)w.mpad;
 #pragma unroll 1
     for (int cc = 0; cc < kTcN / 32; ++cc) {
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_skin_kernel(SmplDev m, int n_
   const int fr = lane;
   const int n = f0 + fr;
   const bool n_ok = n < n_end;
-  const float* vp = w.vpT + (size_t)(vtile * kVTile + vbase) * 3 * w.mpad + n;      // n < mpad (frames padded to 128)
+  const float* vp = vp_buffer(w) + (size_t)(vtile * kVTile + vbase) * 3 * w.mpad + n;      // n < mpad (frames padded to 128)
   mbar_wait(abar, 0);
   constexpr int U = 4;
 #pragma unroll 1
@@ -616,6 +617,7 @@ __global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int 
       mbar_expect_tx(full_w, kSkWBytes);
       tma_bulk_g2s(Ws, m.skW + (size_t)vtile * kSkWImageFloats, kSkWBytes, full_w);          // model constant: before the dependency wait
       pdl_wait();                                                                           // skB (pose prep) and v_posed (blend) below
+      const float* const vpb = vp_buffer(w);
       for (int it = 0; it < ntiles; ++it) {
         const int ftile = ftile0 + it;
         if (it > 0) mbar_wait(b_empty, (it - 1) & 1);
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int 
         tma_bulk_g2s(Bs, w.skB + (size_t)ftile * kSkBImageFloats, kSkBBytes, full_b);
         if (it > 0) mbar_wait(v_empty, (it - 1) & 1);
         mbar_expect_tx(full_v, kSkVBytes);
-        tma_bulk_g2s(Vs, w.vpT + ((size_t)ftile * kTcCols + (size_t)vtile * kTileCols) * kSkF, kSkVBytes, full_v);
+        tma_bulk_g2s(Vs, vpb + ((size_t)ftile * kTcCols + (size_t)vtile * kTileCols) * kSkF, kSkVBytes, full_v);
       }
     }
   } else if (warp == 1) {
@@ -779,10 +781,33 @@ int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* 
 
 // pdl: launch with the programmatic-serialization attribute.  Only for callers whose betas are long-lived constants
 // (the optimiser): the kernel reads betas / shapedirs / posedirs BEFORE it waits for the preceding grid.
+// An SM runs with ONE L1 / shared-memory split at a time.  blend_features_kernel / pose_prep_kernel have no dynamic shared memory, so by
+// default they run with a small shared-memory split, and the GEMM kernel that follows each of them in its stream (2 x 96-101 KB per SM)
+// can only be placed on an SM after the small kernel's CTAs have drained and the SM has been re-configured.  Asking for the maximal
+// shared-memory split on the small SMPL kernels too removes that hand-over: 193.0 -> 157.4 us per iteration at 4 x 300 frame-persons
+// (no change at 1 x 300).  The optimiser's own small kernels lose more from the smaller L1 than they gain (bit 4: +6 us at 1 x 300).
+// GLAMR_SMEM_CARVEOUT bit mask: which kernels ask for the maximal shared-memory split (cudaFuncAttributePreferredSharedMemoryCarveout):
+// 1 = the two LBS GEMM kernels, 2 = the small SMPL kernels next to them, 4 = the optimiser's small kernels (globalopt_kernels.cu)
+int smem_carveout_mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GLAMR_SMEM_CARVEOUT");
+    v = e ? atoi(e) : GLAMR_DEFAULT_SMEM_CARVEOUT;
+  }
+  return v;
+}
 static int lbs_set_attrs() {
   static bool attrs = false;
   if (!attrs) {
     attrs = true;
+    if (smem_carveout_mask() & 1) {
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_blend_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    if (smem_carveout_mask() & 2) {
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(blend_features_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      GLAMR_CUDA_TRY(cudaFuncSetAttribute(pose_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
     GLAMR_CUDA_TRY(cudaFuncSetAttribute(lbs_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmemBytes));
