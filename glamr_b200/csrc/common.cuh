@@ -32,6 +32,7 @@
 #define GLAMR_DEFAULT_ITER_FUSED 0
 #define GLAMR_DEFAULT_LBS_TC 2        /* 2 = tensor-core blend + tensor-core skinning (verified on B200: all GPU tests green, memcheck clean), 1 = tensor-core blend + SIMT skinning, 0 = FP32 SIMT kernel */
 #define GLAMR_DEFAULT_BLEND_EARLY 0    /* 1: pipelined blend at the top of the evaluation into a second v_posed buffer -- measured slower (it takes the SMs the skinning needs: 98.8 vs 88.0 us at 1 x 300), kept selectable (GLAMR_BLEND_EARLY=1) */
+#define GLAMR_DEFAULT_BLEND_SPLIT 0    /* percent of the pipelined blend launched at the top of the evaluation (GLAMR_BLEND_SPLIT) */
 #define GLAMR_DEFAULT_SMEM_CARVEOUT 3   /* bit mask, see smem_carveout_mask() in smpl_kernels.cu: measured 193.0 -> 157.4 us per iteration at 4 x 300, neutral at 1 x 300 */
 #define GLAMR_DEFAULT_NET_WIMG 0       /* prior-network GEMMs: weight operand as a pre-split image fetched by bulk TMA (GLAMR_NET_WIMG=1) */
 

@@ -659,6 +659,7 @@ struct glamr_opt {
   cudaStream_t aux;
   cudaEvent_t ev_fork, ev_join;
   int vpt_ready;
+  int blend_split;            // percent of the pipelined blend's frame tiles launched at the top of the evaluation (0: none)
   int blend_early;            // the pipelined blend is launched at the top of the evaluation into the other v_posed buffer
   cudaEvent_t ev[24];         // timing == 2: one event after every launch of glamr_opt_backward / glamr_opt_apply
   int n_ev;
@@ -722,9 +723,15 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
     // second v_posed buffer); the fused iteration advances the step count inside its tail kernel and keeps the single buffer
     const char* e = getenv("GLAMR_BLEND_EARLY");
     st->blend_early = (e ? atoi(e) != 0 : GLAMR_DEFAULT_BLEND_EARLY != 0) && !st->fused;
+    // GLAMR_BLEND_SPLIT=<percent>: launch that share of the pipelined blend's 128-frame tiles at the TOP of the evaluation, where the GPU
+    // only runs the latency-bound trajectory / pose kernels, and the rest after the skinning (0: everything after the skinning).
+    // Needs the second v_posed buffer like GLAMR_BLEND_EARLY.
+    const char* sp = getenv("GLAMR_BLEND_SPLIT");
+    st->blend_split = st->fused || st->blend_early ? 0 : (sp ? atoi(sp) : GLAMR_DEFAULT_BLEND_SPLIT);
+    if (st->blend_split < 0 || st->blend_split > 100) st->blend_split = 0;
   }
   const size_t n128 = (N + kTcM - 1) / kTcM * kTcM;
-  const size_t o_vp2 = st->blend_early ? take((size_t)kTcCols * ((n128 + kSkF - 1) / kSkF * kSkF)) : 0;        // second v_posed buffer (pipelined blend)
+  const size_t o_vp2 = (st->blend_early || st->blend_split > 0) ? take((size_t)kTcCols * ((n128 + kSkF - 1) / kSkF * kSkF)) : 0;        // second v_posed buffer (pipelined blend)
   st->arena_bytes = floats * sizeof(float);
   cudaError_t e = cudaMalloc(&st->arena, st->arena_bytes);
   if (e != cudaSuccess) { free(st); return (int)e; }
@@ -743,7 +750,7 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
   st->sc.grad = nullptr;
   st->adam.m = b + o_m; st->adam.v = b + o_v;
   st->ws = smpl_carve_workspace(b + o_ws, (int)N, smpl->dev.S);
-  if (st->blend_early) {
+  if (st->blend_early || st->blend_split > 0) {
     st->ws.vpT2 = b + o_vp2;
     st->ws.flip_src = st->adam.beta_pow + 2;
   }
@@ -933,19 +940,29 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   const float* const pose_l = pb.smpl_pose_all + (size_t)n_begin * 69;
   const float* const beta_l = pb.smpl_beta_all + (size_t)n_begin * kNB;
   // the blend of the NEXT evaluation (it depends on body pose / betas only): side stream, concurrent with this evaluation
-  auto fork_blend = [&]() -> int {
+  // part 0: the whole blend; part 1: the features + the first `mt_split` frame tiles; part 2: the remaining tiles
+  const int mt_all = (n_end - n_begin + kTcM - 1) / kTcM;
+  int mt_split = 0;
+  if (st->blend_split > 0 && !st->timing && mt_all > 1) {
+    mt_split = (mt_all * st->blend_split + 50) / 100;
+    if (mt_split < 1) mt_split = 1;
+    if (mt_split > mt_all - 1) mt_split = mt_all - 1;
+  }
+  auto fork_blend = [&](int part) -> int {
     SmplWorkspace wn = wo;
     wn.flip_add = 1;                           // with two buffers: the one the next step's skinning will read
     GLAMR_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
     GLAMR_CUDA_TRY(cudaStreamWaitEvent(st->aux, st->ev_fork, 0));
-    if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend0, st->aux));
+    if (st->timing && part != 2) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend0, st->aux));
     if (!(exp_skip & 1)) {
-      const int rc = launch_blend(st->smpl, n_end - n_begin, pose_l, beta_l, wn, st->aux);
+      const int rc = launch_blend(st->smpl, n_end - n_begin, pose_l, beta_l, wn, st->aux, part == 2 ? mt_split : 0, part == 1 ? mt_split : -1, part != 2);
       if (rc) return rc;
     }
-    if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend1, st->aux));
-    GLAMR_CUDA_TRY(cudaEventRecord(st->ev_join, st->aux));
-    forked = true;
+    if (part != 1) {
+      if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_blend1, st->aux));
+      GLAMR_CUDA_TRY(cudaEventRecord(st->ev_join, st->aux));
+      forked = true;
+    }
     return GLAMR_OK;
   };
   if (tc && n_end > n_begin) {
@@ -954,8 +971,8 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
       if (rc) return rc;
       st->vpt_ready = 1;
     }
-    if (st->blend_early) {
-      const int rc = fork_blend();
+    if (st->blend_early || mt_split > 0) {
+      const int rc = fork_blend(st->blend_early ? 0 : 1);
       if (rc) return rc;
     }
   }
@@ -986,8 +1003,8 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
       if (!(exp_skip & 2))
         if ((rc = launch_skin(st->smpl, nn, wo, nullptr, s))) return rc;
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
-      if (!st->blend_early)                 // single buffer: the next blend may only start once this skinning has read v_posed
-        if ((rc = fork_blend())) return rc;
+      if (!st->blend_early)                 // the (rest of the) next blend: with a single buffer it may only start once this skinning has read v_posed
+        if ((rc = fork_blend(mt_split > 0 ? 2 : 0))) return rc;
     } else {
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
       if ((rc = launch_lbs(st->smpl, 0, nn, beta_l, wo, nullptr, s, true))) return rc;

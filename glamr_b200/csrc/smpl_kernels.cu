@@ -347,7 +347,7 @@ constexpr uint32_t kTcABytes = kTcAStageFloats * sizeof(float);      // 8,192
 constexpr uint32_t kTcBBytes = kTcBStageFloats * sizeof(float);      // 16,384
 constexpr size_t kTcSmemBytes = (size_t)kTcStages * (kTcABytes + kTcBBytes) + 128;
 
-__global__ void __launch_bounds__(kTcThreads) lbs_blend_tc_kernel(SmplDev m, SmplWorkspace w) {
+__global__ void __launch_bounds__(kTcThreads) lbs_blend_tc_kernel(SmplDev m, SmplWorkspace w, int mtile0) {
   extern __shared__ __align__(128) unsigned char tc_raw[];
   float* As = reinterpret_cast<float*>(tc_raw);                                   // [stages][hi | lo][2][128][4]
   float* Bs = As + kTcStages * kTcAStageFloats;                                   // [stages][hi | lo][2][256][4]
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kTcThreads) lbs_blend_tc_kernel(SmplDev m, Smp
   uint64_t* acc_full = empty + kTcStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntile = blockIdx.x, mtile = blockIdx.y;
+  const int ntile = blockIdx.x, mtile = blockIdx.y + mtile0;     // mtile0: first 128-frame tile of this launch (the optimiser splits the blend in two launches)
   pdl_launch_dependents();
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcN));
@@ -573,9 +573,15 @@ constexpr size_t kSkinTcSmemBytes = (size_t)kSkWBytes + kSkBBytes + kSkVBytes + 
                  "=r"((v)[8]), "=r"((v)[9]), "=r"((v)[10]), "=r"((v)[11]), "=r"((v)[12]), "=r"((v)[13]), "=r"((v)[14]), "=r"((v)[15])  \
                : "r"(taddr))
 
+#define GLAMR_TMEM_LD_X8(v, taddr)                                                                                  \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"                      \
+               : "=r"((v)[0]), "=r"((v)[1]), "=r"((v)[2]), "=r"((v)[3]), "=r"((v)[4]), "=r"((v)[5]), "=r"((v)[6]), "=r"((v)[7]) \
+               : "r"(taddr))
+
+constexpr int kSkinTcThreads = 320;     // warp 0 producer, warp 1 TMEM + MMA, warps 2-9 epilogue (two warps per TMEM lane quarter)
 constexpr int kSkTilesPerCta = 3;       // frame tiles one CTA sweeps (W stays in shared memory; 54 x 5 CTAs = one wave at 300 frames)
 
-__global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int n, SmplWorkspace w, float* __restrict__ vertices) {
+__global__ void __launch_bounds__(kSkinTcThreads) lbs_skin_tc_kernel(SmplDev m, int n, SmplWorkspace w, float* __restrict__ vertices) {
   extern __shared__ __align__(128) unsigned char sk_raw[];
   float* Ws = reinterpret_cast<float*>(sk_raw);                       // [hi | lo][6][128][4]
   float* Bs = Ws + kSkWImageFloats;                                   // [hi | lo][6][240][4]
@@ -603,8 +609,8 @@ __global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int 
     mbar_init(full_v, 1);
     mbar_init(acc_full, 1);
     mbar_init(b_empty, 1);
-    mbar_init(v_empty, 4);
-    mbar_init(acc_empty, 4);
+    mbar_init(v_empty, 8);
+    mbar_init(acc_empty, 8);
     mbar_fence_init();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -652,8 +658,9 @@ __global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int 
       }
     }
   } else {
-    // ---- epilogue: warp q = warp % 4 reads TMEM lanes 32 q .. 32 q + 31 (= vertices of this tile)
-    const int q = warp & 3;
+    // ---- epilogue: warp q = warp % 4 may read TMEM lanes 32 q .. 32 q + 31 (= vertices of this tile); the two warps of a quarter take
+    // alternate pairs of frames (24 accumulator columns each)
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int vl = q * 32 + lane;
     const int gv = vtile * kVTile + vl;
     const bool v_ok = gv < kV;
@@ -665,20 +672,19 @@ __global__ void __launch_bounds__(kTcThreads) lbs_skin_tc_kernel(SmplDev m, int 
       mbar_wait(acc_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int g = 0; g < kSkF / 4; ++g) {                         // 4 frames = 48 accumulator columns per step
-        uint32_t t[48];
-        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 48);
+      for (int g = half; g < kSkF / 2; g += 2) {                   // 2 frames = 24 accumulator columns per step
+        uint32_t t[24];
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 24);
         GLAMR_TMEM_LD_X16(t, taddr);
-        GLAMR_TMEM_LD_X16(t + 16, taddr + 16);
-        GLAMR_TMEM_LD_X16(t + 32, taddr + 32);
-        const float4 xs = *reinterpret_cast<const float4*>(vrow + g * 4);
-        const float4 ys = *reinterpret_cast<const float4*>(vrow + kSkF + g * 4);
-        const float4 zs = *reinterpret_cast<const float4*>(vrow + 2 * kSkF + g * 4);
+        GLAMR_TMEM_LD_X8(t + 16, taddr + 16);
+        const float2 xs = *reinterpret_cast<const float2*>(vrow + g * 2);
+        const float2 ys = *reinterpret_cast<const float2*>(vrow + kSkF + g * 2);
+        const float2 zs = *reinterpret_cast<const float2*>(vrow + 2 * kSkF + g * 2);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float x[4] = {xs.x, xs.y, xs.z, xs.w}, y[4] = {ys.x, ys.y, ys.z, ys.w}, z[4] = {zs.x, zs.y, zs.z, zs.w};
+        const float x[2] = {xs.x, xs.y}, y[2] = {ys.x, ys.y}, z[2] = {zs.x, zs.y};
 #pragma unroll
-        for (int ff = 0; ff < 4; ++ff) {
-          const int fl = ftile * kSkF + g * 4 + ff;                // local frame-person index
+        for (int ff = 0; ff < 2; ++ff) {
+          const int fl = ftile * kSkF + g * 2 + ff;                // local frame-person index
 #define GLAMR_T(k) __uint_as_float(t[ff * 12 + (k)])
           const float ox = fmaf(GLAMR_T(0), x[ff], fmaf(GLAMR_T(1), y[ff], fmaf(GLAMR_T(2), z[ff], GLAMR_T(3))));
           const float oy = fmaf(GLAMR_T(4), x[ff], fmaf(GLAMR_T(5), y[ff], fmaf(GLAMR_T(6), z[ff], GLAMR_T(7))));
@@ -816,14 +822,22 @@ static int lbs_set_attrs() {
   return GLAMR_OK;
 }
 // blend features + blend GEMM for local frame-persons [0, n): v_posed (transposed) of the workspace
-int launch_blend(const SmplDev& m, int n, const float* body_pose, const float* betas, const SmplWorkspace& w, cudaStream_t s) {
+// mt_begin / mt_end: the range of 128-frame tiles of the GEMM this call launches (mt_end < 0: all); features: also (re)build the A operand
+int launch_blend(const SmplDev& m, int n, const float* body_pose, const float* betas, const SmplWorkspace& w, cudaStream_t s, int mt_begin,
+                 int mt_end, bool features) {
   if (n <= 0) return GLAMR_OK;
   int rc;
   if ((rc = lbs_set_attrs())) return rc;
-  blend_features_kernel<<<(n + 3) / 4, 128, 0, s>>>(n, body_pose, betas, w);
-  GLAMR_LAUNCH_CHECK();
-  lbs_blend_tc_kernel<<<dim3(kTcNTiles, (n + kTcM - 1) / kTcM), kTcThreads, kTcSmemBytes, s>>>(m, w);
-  GLAMR_LAUNCH_CHECK();
+  const int mtiles = (n + kTcM - 1) / kTcM;
+  if (mt_end < 0 || mt_end > mtiles) mt_end = mtiles;
+  if (features) {
+    blend_features_kernel<<<(n + 3) / 4, 128, 0, s>>>(n, body_pose, betas, w);
+    GLAMR_LAUNCH_CHECK();
+  }
+  if (mt_end > mt_begin) {
+    lbs_blend_tc_kernel<<<dim3(kTcNTiles, mt_end - mt_begin), kTcThreads, kTcSmemBytes, s>>>(m, w, mt_begin);
+    GLAMR_LAUNCH_CHECK();
+  }
   return GLAMR_OK;
 }
 // skinning of local frame-persons [0, n) from the workspace's v_posed and A
@@ -832,7 +846,7 @@ int launch_skin(const SmplDev& m, int n, const SmplWorkspace& w, float* vertices
   int rc;
   if ((rc = lbs_set_attrs())) return rc;
   if (w.vp_tiled) {
-    lbs_skin_tc_kernel<<<dim3(kNVTiles, ((n + kSkF - 1) / kSkF + kSkTilesPerCta - 1) / kSkTilesPerCta), kTcThreads, kSkinTcSmemBytes, s>>>(m, n, w, vertices);
+    lbs_skin_tc_kernel<<<dim3(kNVTiles, ((n + kSkF - 1) / kSkF + kSkTilesPerCta - 1) / kSkTilesPerCta), kSkinTcThreads, kSkinTcSmemBytes, s>>>(m, n, w, vertices);
     GLAMR_LAUNCH_CHECK();
     return GLAMR_OK;
   }
@@ -868,22 +882,22 @@ int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, con
     if (w.vp_tiled) {
       const dim3 sgrid(kNVTiles, ((n_end + kSkF - 1) / kSkF + kSkTilesPerCta - 1) / kSkTilesPerCta);
       if (pdl) {
-        GLAMR_CUDA_TRY(launch_pdl(4, lbs_blend_tc_kernel, dim3(kTcNTiles, mtiles), dim3(kTcThreads), kTcSmemBytes, s, m, w));
-        GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_tc_kernel, sgrid, dim3(kTcThreads), kSkinTcSmemBytes, s, m, n_end, w, vertices));
+        GLAMR_CUDA_TRY(launch_pdl(4, lbs_blend_tc_kernel, dim3(kTcNTiles, mtiles), dim3(kTcThreads), kTcSmemBytes, s, m, w, 0));
+        GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_tc_kernel, sgrid, dim3(kSkinTcThreads), kSkinTcSmemBytes, s, m, n_end, w, vertices));
       } else {
-        lbs_blend_tc_kernel<<<dim3(kTcNTiles, mtiles), kTcThreads, kTcSmemBytes, s>>>(m, w);
+        lbs_blend_tc_kernel<<<dim3(kTcNTiles, mtiles), kTcThreads, kTcSmemBytes, s>>>(m, w, 0);
         GLAMR_LAUNCH_CHECK();
-        lbs_skin_tc_kernel<<<sgrid, kTcThreads, kSkinTcSmemBytes, s>>>(m, n_end, w, vertices);
+        lbs_skin_tc_kernel<<<sgrid, kSkinTcThreads, kSkinTcSmemBytes, s>>>(m, n_end, w, vertices);
         GLAMR_LAUNCH_CHECK();
       }
       return GLAMR_OK;
     }
     if (pdl) {
-      GLAMR_CUDA_TRY(launch_pdl(4, lbs_blend_tc_kernel, dim3(kTcNTiles, mtiles), dim3(kTcThreads), kTcSmemBytes, s, m, w));
+      GLAMR_CUDA_TRY(launch_pdl(4, lbs_blend_tc_kernel, dim3(kTcNTiles, mtiles), dim3(kTcThreads), kTcSmemBytes, s, m, w, 0));
       if (m.K == 4) GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_kernel<4>, grid, dim3(kLbsThreads), kSkinSmemBytes, s, m, n_begin, n_end, w, vertices));
       else GLAMR_CUDA_TRY(launch_pdl(4, lbs_skin_kernel<0>, grid, dim3(kLbsThreads), kSkinSmemBytes, s, m, n_begin, n_end, w, vertices));
     } else {
-      lbs_blend_tc_kernel<<<dim3(kTcNTiles, mtiles), kTcThreads, kTcSmemBytes, s>>>(m, w);
+      lbs_blend_tc_kernel<<<dim3(kTcNTiles, mtiles), kTcThreads, kTcSmemBytes, s>>>(m, w, 0);
       GLAMR_LAUNCH_CHECK();
       if (m.K == 4) lbs_skin_kernel<4><<<grid, kLbsThreads, kSkinSmemBytes, s>>>(m, n_begin, n_end, w, vertices);
       else lbs_skin_kernel<0><<<grid, kLbsThreads, kSkinSmemBytes, s>>>(m, n_begin, n_end, w, vertices);

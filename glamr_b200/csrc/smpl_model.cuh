@@ -237,7 +237,8 @@ int launch_pose_prep(const SmplDev& m, int n, const float* orient, const float* 
 int launch_lbs(const SmplDev& m, int n_begin, int n_end, const float* betas, const SmplWorkspace& w, float* vertices,
                cudaStream_t s, bool pdl = false);
 // tensor-core path in two halves (the optimiser pipelines them: the blend depends on body pose / betas only)
-int launch_blend(const SmplDev& m, int n, const float* body_pose, const float* betas, const SmplWorkspace& w, cudaStream_t s);
+int launch_blend(const SmplDev& m, int n, const float* body_pose, const float* betas, const SmplWorkspace& w, cudaStream_t s, int mt_begin = 0,
+                 int mt_end = -1, bool features = true);
 int launch_skin(const SmplDev& m, int n, const SmplWorkspace& w, float* vertices, cudaStream_t s);
 int smem_carveout_mask();                    // GLAMR_SMEM_CARVEOUT (see smpl_kernels.cu)
 int lbs_kernel_count(const SmplDev& m);      // kernels one launch_lbs call launches
