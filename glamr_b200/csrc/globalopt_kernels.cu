@@ -659,6 +659,7 @@ struct glamr_opt {
   cudaStream_t aux;
   cudaEvent_t ev_fork, ev_join;
   int vpt_ready;
+  int features_early;         // the pipelined blend's feature kernel runs at the top of the evaluation
   int blend_split;            // percent of the pipelined blend's frame tiles launched at the top of the evaluation (0: none)
   int blend_early;            // the pipelined blend is launched at the top of the evaluation into the other v_posed buffer
   cudaEvent_t ev[24];         // timing == 2: one event after every launch of glamr_opt_backward / glamr_opt_apply
@@ -729,6 +730,16 @@ extern "C" int glamr_opt_create(glamr_opt_t** out, const glamr_smpl_t* smpl, con
     const char* sp = getenv("GLAMR_BLEND_SPLIT");
     st->blend_split = st->fused || st->blend_early ? 0 : (sp ? atoi(sp) : GLAMR_DEFAULT_BLEND_SPLIT);
     if (st->blend_split < 0 || st->blend_split > 100) st->blend_split = 0;
+    // GLAMR_FEATURES_EARLY=0|1: the feature kernel of the pipelined blend (its A operand; body pose / betas only) runs at the top of the
+    // evaluation on the side stream, so that only the GEMM is left after the skinning
+    // (default: only while this rank's per-frame kernels have fewer CTAs than the GPU has SMs -- measured 102.8 -> 94.8 us per L2-flushed
+    // iteration at 1 x 300, but 154 -> 180 us at 4 x 300, where the GEMM then no longer follows a kernel with its own shared-memory split)
+    const char* fe = getenv("GLAMR_FEATURES_EARLY");
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int frame_ctas = (pb->n_end - pb->n_begin + kFrameThreads / 32 - 1) / (kFrameThreads / 32);
+    st->features_early = (fe ? atoi(fe) != 0 : frame_ctas < sms) && !st->fused;
   }
   const size_t n128 = (N + kTcM - 1) / kTcM * kTcM;
   const size_t o_vp2 = (st->blend_early || st->blend_split > 0) ? take((size_t)kTcCols * ((n128 + kSkF - 1) / kSkF * kSkF)) : 0;        // second v_posed buffer (pipelined blend)
@@ -942,11 +953,13 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
   // the blend of the NEXT evaluation (it depends on body pose / betas only): side stream, concurrent with this evaluation
   // part 0: the whole blend; part 1: the features + the first `mt_split` frame tiles; part 2: the remaining tiles
   const int mt_all = (n_end - n_begin + kTcM - 1) / kTcM;
-  int mt_split = 0;
+  int mt_split = -1;                            // -1: one launch sequence after the skinning; >= 0: features (+ mt_split tiles) at the top
   if (st->blend_split > 0 && !st->timing && mt_all > 1) {
     mt_split = (mt_all * st->blend_split + 50) / 100;
     if (mt_split < 1) mt_split = 1;
     if (mt_split > mt_all - 1) mt_split = mt_all - 1;
+  } else if (st->features_early && !st->timing && !st->blend_early) {
+    mt_split = 0;                               // only the (tiny) feature kernel moves to the top: the GEMM's operand is ready when the skinning ends
   }
   auto fork_blend = [&](int part) -> int {
     SmplWorkspace wn = wo;
@@ -971,7 +984,7 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
       if (rc) return rc;
       st->vpt_ready = 1;
     }
-    if (st->blend_early || mt_split > 0) {
+    if (st->blend_early || mt_split >= 0) {
       const int rc = fork_blend(st->blend_early ? 0 : 1);
       if (rc) return rc;
     }
@@ -1004,7 +1017,7 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
         if ((rc = launch_skin(st->smpl, nn, wo, nullptr, s))) return rc;
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs1, s));
       if (!st->blend_early)                 // the (rest of the) next blend: with a single buffer it may only start once this skinning has read v_posed
-        if ((rc = fork_blend(mt_split > 0 ? 2 : 0))) return rc;
+        if ((rc = fork_blend(mt_split >= 0 ? 2 : 0))) return rc;
     } else {
       if (st->timing) GLAMR_CUDA_TRY(cudaEventRecord(st->ev_lbs0, s));
       if ((rc = launch_lbs(st->smpl, 0, nn, beta_l, wo, nullptr, s, true))) return rc;
