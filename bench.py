@@ -40,7 +40,7 @@ FLOPS_PER_FP = 15.85e6            # dense full-LBS forward (al
 FLOPS_PER_FP_EXECUTED = 9.8e6     # K-sparse skinning (4 weights per vertex): what the kernel really issues
 REF_BUDGET_S = float(os.environ.get('GLAMR_REF_BUDGET_S', 150.0))   # wall-clock bound (s) of the CPU reference arm (--impl reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of one LBS launch, keyed by frame-persons per launch (ncu capture, profiles/)
-NCU_LBS_DRAM_BYTES = {300: 37885952 + 3018752 + 26944768}     # blend (read + write) + tensor-core skinning (read), profiles/lbs_skin_tc_r02.md
+NCU_LBS_DRAM_BYTES = {300: 37911808 + 2394624 + 26944768}     # blend (read + write) + tensor-core skinning (read), profiles/lbs_tc_kernels_r02_final.md
 # switches that change what the library executes: the bench refuses to run with any of them set
 FORBIDDEN_ENV = ['GLAMR_B200_SO', 'GLAMR_LBS_DEBUG', 'GLAMR_TC_DEBUG', 'GLAMR_PDL', 'GLAMR_LBS_STAGES', 'GLAMR_TC_NTILE']
 ECHO_ENV = FORBIDDEN_ENV + ['GLAMR_ITER_PATH', 'GLAMR_LBS_PATH', 'GLAMR_PRIOR_GRAPH', 'GLAMR_NET_WIMG', 'GLAMR_NET_SKINNY', 'GLAMR_ALLREDUCE', 'OMP_NUM_THREADS', 'NCCL_ALGO', 'NCCL_PROTO']
@@ -665,7 +665,7 @@ def run_ours(args):
                              'peak_tflops_tf32': peaks.get('bf16_tflops', 2250.0) / 2,
                              'frac': 3 * 2 * 224 * 20736 * (-(-n_local // 128) * 128) / (blend_ms * 1e-3) / 1e12 / (peaks.get('bf16_tflops', 2250.0) / 2),
                              'note': '3xTF32: three kind::tf32 MMAs per product; peak = half of the measured dense bf16 throughput (MEASURED_PEAKS.json); '
-                                     'ncu: sm__pipe_tensor_cycles_active 56.6 % of peak, 167 MB L2->SM per launch (profiles/lbs_blend_tc_r02.md)'},
+                                     'ncu: sm__pipe_tensor_cycles_active 56.6 % of peak, 167 MB L2->SM per launch (profiles/lbs_tc_kernels_r02_final.md)'},
                          'fp32': {'achieved_tflops': fp32_tf, 'executed_tflops': fp32_exec, 'peak_tflops': fp32_peak, 'frac': fp32_tf / fp32_peak, 'frac_executed': fp32_exec / fp32_peak,
                                   'peak_source': 'glamr_fp32_probe: register-resident FFMA loop timed in this run (best of 5)',
                                   'note': 'algorithmic LBS flops (15.85 MFLOP per frame-person, dense skinning) over the LBS time (blend GEMM timed in situ on its side stream + skinning kernel) against the measured FP32 FFMA peak; '
