@@ -323,7 +323,7 @@ class StageLoop:
                                               1, 0, L.stream_ptr()), 'iterate')
         else:
             def iteration():
-                model._backward()            # backward pass + NCCL all-reduce of [grad | term sums]
+                model._backward(for_apply=True)            # backward pass + NCCL all-reduce of [grad | term sums]
                 L.check(lib.glamr_opt_apply(model._opt, L.ptr(model._theta), L.ptr(model._reduce), lr, L.ptr(self.hist), L.NUM_TERMS + 1,
                                             L.stream_ptr()), 'apply')
         self.iteration = iteration

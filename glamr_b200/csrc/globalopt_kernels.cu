@@ -659,6 +659,7 @@ struct glamr_opt {
   cudaStream_t aux;
   cudaEvent_t ev_fork, ev_join;
   int vpt_ready;
+  int join_pending;           // a glamr_opt_backward_for_apply call left the side stream un-joined (the next call on the handle joins)
   int features_early;         // the pipelined blend's feature kernel runs at the top of the evaluation
   int blend_split;            // percent of the pipelined blend's frame tiles launched at the top of the evaluation (0: none)
   int blend_early;            // the pipelined blend is launched at the top of the evaluation into the other v_posed buffer
@@ -860,9 +861,15 @@ extern "C" int glamr_opt_destroy(glamr_opt_t* st) {
   return GLAMR_OK;
 }
 
+static int join_pending(glamr_opt_t* st, cudaStream_t s);
+
 extern "C" int glamr_opt_set_problem(glamr_opt_t* st, const glamr_problem_t* pb, int reset_adam, void* stream) {
   if (!st || !pb) return GLAMR_EINVAL;
   if (pb->P != st->pb.P || pb->T != st->pb.T || pb->J != st->pb.J || pb->n_params != st->pb.n_params) return GLAMR_EINVAL;
+  {
+    const int rc = join_pending(st, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   st->pb = *pb;
   st->gen++;
   compute_gs(st);
@@ -898,11 +905,27 @@ extern "C" int glamr_opt_launch_count(const glamr_opt_t* st, int via_iterate) {
 
 struct FusedAdam { float* theta; double lr; float* loss_terms; int hist_stride; };
 
-static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream, bool use_peers, const FusedAdam* adam = nullptr) {
+// the side stream's work of an earlier evaluation whose join was left to the next call on the handle
+static int join_pending(glamr_opt_t* st, cudaStream_t s) {
+  if (st->join_pending) {
+    GLAMR_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join, 0));
+    st->join_pending = 0;
+  }
+  return GLAMR_OK;
+}
+
+// defer_join: the caller runs glamr_opt_apply on the same handle next (possibly after an exchange of reduce_buf): the pipelined blend on the
+// side stream is joined there, so that the exchange overlaps its tail instead of waiting for it
+static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream, bool use_peers, const FusedAdam* adam = nullptr,
+                         bool defer_join = false) {
   if (!st || !theta || !reduce_buf) return GLAMR_EINVAL;
   PeerCtx pc = st->peer;
   if (!use_peers) pc.world = 0;
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const int rc = join_pending(st, s);
+    if (rc) return rc;
+  }
   st->n_ev = 0;
   GLAMR_MARK();
   const glamr_problem_t& pb = st->pb;
@@ -1054,11 +1077,20 @@ static int backward_impl(glamr_opt_t* st, const float* theta, float* reduce_buf,
     GLAMR_CUDA_TRY(launch_pdl(16, traj_cam_backward_kernel, dim3(pb.P + st->cam_blocks), dim3(kScanThreads), 0, s, c, from_persons ? 0 : 1, part_traj,
                               (const double*)st->partial, n_slots, reduce_buf, st->tickets, pc));
   GLAMR_MARK();
-  if (forked) GLAMR_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join, 0));      // the side stream rejoins before the evaluation ends
+  if (forked) {
+    if (defer_join) st->join_pending = 1;
+    else GLAMR_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join, 0));      // the side stream rejoins before the evaluation ends
+  }
   return GLAMR_OK;
 }
 extern "C" int glamr_opt_backward(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream) {
   return backward_impl(st, theta, reduce_buf, stream, false);
+}
+// The first half of an iteration whose second half is glamr_opt_apply on the same stream (with the caller's exchange of reduce_buf in
+// between): same work as glamr_opt_backward, but the side-stream blend of the next evaluation is joined by that apply call (or by the next
+// call on the handle), so the exchange runs next to its tail.
+extern "C" int glamr_opt_backward_for_apply(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream) {
+  return backward_impl(st, theta, reduce_buf, stream, false, nullptr, true);
 }
 
 extern "C" int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms, void* stream) {
@@ -1075,6 +1107,10 @@ static int apply_impl(glamr_opt_t* st, float* theta, const float* reduce_buf, do
   PeerCtx pc = st->peer;
   if (!use_peers) pc.world = 0;
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const int rc = join_pending(st, s);
+    if (rc) return rc;
+  }
   OptCtx c = make_ctx(st, theta, nullptr);
   const int blocks = (st->pb.n_params + 255) / 256;
   GLAMR_CUDA_TRY(launch_pdl(32, apply_kernel, dim3(blocks < 296 ? blocks : 296), dim3(256), 0, s, c, theta, reduce_buf, lr, st->adam, loss_terms,

@@ -601,8 +601,11 @@ class GlobalReconOptimizer:
                 L.check(self._lib.glamr_opt_set_problem(self._opt, ctypes.byref(pb), flags, L.stream_ptr()), 'glamr_opt_set_problem')
         self._fresh_attach = False
 
-    def _backward(self):
-        L.check(self._lib.glamr_opt_backward(self._opt, L.ptr(self._theta), L.ptr(self._reduce), L.stream_ptr()), 'glamr_opt_backward')
+    def _backward(self, for_apply=False):
+        """for_apply: glamr_opt_apply follows on this stream (the optimisation loop); the library then joins its side stream there, so the
+        exchange below overlaps the tail of the pipelined blend"""
+        fn = self._lib.glamr_opt_backward_for_apply if for_apply else self._lib.glamr_opt_backward
+        L.check(fn(self._opt, L.ptr(self._theta), L.ptr(self._reduce), L.stream_ptr()), 'glamr_opt_backward')
         if self.world > 1:                                     # the one collective of the path: packed gradient + term sums
             if getattr(self, '_peer_ok', False):              # one-shot NVLink all-reduce of the library (no NCCL call)
                 L.check(self._lib.glamr_allreduce_inplace(self._opt, L.ptr(self._reduce), self._reduce.numel(), L.stream_ptr()), 'glamr_allreduce_inplace')
@@ -683,7 +686,7 @@ class GlobalReconOptimizer:
             stream = torch.cuda.current_stream()
 
             def one_iteration():
-                self._backward()
+                self._backward(for_apply=True)
                 L.check(lib.glamr_opt_apply(self._opt, L.ptr(self._theta), L.ptr(self._reduce), float(opt_lr), L.ptr(hist), NUM_TERMS + 1,
                                             L.stream_ptr()), 'glamr_opt_apply')
             graph = None

@@ -251,6 +251,9 @@ int glamr_opt_losses(glamr_opt_t* st, const float* reduce_buf, float* loss_terms
 /* Measurement hooks (bench.py roofline): when enabled, glamr_opt_backward brackets the LBS kernel with CUDA events on
  * the launching stream (do not enable while capturing a CUDA graph); glamr_opt_last_lbs_ms waits for the last pair
  * and returns its duration.  The only entry point that synchronises. */
+/* glamr_opt_backward for a caller that runs glamr_opt_apply next on the same stream, with its exchange of reduce_buf in between (the
+ * multi-GPU loop of global_recon_model.py:558-569): the pipelined side-stream work is joined by that apply call, not at the end of this one */
+int glamr_opt_backward_for_apply(glamr_opt_t* st, const float* theta, float* reduce_buf, void* stream);
 int glamr_opt_kernel_timing(glamr_opt_t* st, int enable);
 /* the last timed evaluation split into the critical-path kernel (skinning; whole LBS kernel on the SIMT path) and the side-stream blend */
 int glamr_opt_last_lbs_parts_ms(glamr_opt_t* st, float* critical_ms, float* blend_ms);
