@@ -40,6 +40,7 @@ FLOPS_PER_FP = 15.85e6            # dense full-LBS forward (al
 FLOPS_PER_FP_EXECUTED = 9.8e6     # K-sparse skinning (4 weights per vertex): what the kernel really issues
 REF_BUDGET_S = float(os.environ.get('GLAMR_REF_BUDGET_S', 150.0))   # wall-clock bound (s) of the CPU reference arm (--impl reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of one LBS launch, keyed by frame-persons per launch (ncu capture, profiles/)
+NCU_BLEND_DRAM_BYTES = {300: 37911808 + 2394624}               # lbs_blend_tc_kernel alone
 NCU_LBS_DRAM_BYTES = {300: 37911808 + 2394624 + 26944768}     # blend (read + write) + tensor-core skinning (read), profiles/lbs_tc_kernels_r02_final.md
 # switches that change what the library executes: the bench refuses to run with any of them set
 FORBIDDEN_ENV = ['GLAMR_B200_SO', 'GLAMR_LBS_DEBUG', 'GLAMR_TC_DEBUG', 'GLAMR_PDL', 'GLAMR_LBS_STAGES', 'GLAMR_TC_NTILE']
@@ -634,24 +635,7 @@ def run_ours(args):
         achieved = alg_bytes / (lbs_ms * 1e-3) / 1e9
         fp32_tf = FLOPS_PER_FP * n_local / (lbs_ms * 1e-3) / 1e12
         fp32_exec = FLOPS_PER_FP_EXECUTED * n_local / (lbs_ms * 1e-3) / 1e12
-        res = {
-            'metric': 'global_opt_frame_person_iterations_per_sec', 'value': units / (cold_ms * 1e-3), 'unit': 'frame*person*iter/s',
-            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': cold_ms, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'iters_per_sec': 1e3 / cold_ms,
-            'value_l2_warm': units / (warm_ms * 1e-3), 'ms_per_step_l2_warm': warm_ms,
-            'config': {'workload': f'{CFG_ID}:init_opt, {persons} person(s) x {args.frames} frames, full-LBS every iteration',
-                       'persons': persons, 'frames': args.frames,
-                       'parallelism': (f'frame-persons sharded over {world} GPU(s), ' + ('gradient reduction over NVLink peer memory fused into the Adam kernel' if peer else '1 NCCL allreduce/iter')) if world > 1 else 'single GPU',
-                       'l2': 'flushed between timed iterations (256 MiB fill); value_l2_warm = back-to-back replays',
-                       'cuda_graph': graph_on, 'prior': 'CUDA infiller+traj-pred with seeded stand-in weights (no checkpoints offline), latents injected',
-                       'env': {k: os.environ.get(k) for k in ECHO_ENV if os.environ.get(k) is not None}},
-            'clocks': clocks,
-            'gpu_launches': launches_per_iter * K,
-            'gpu_launches_per_step': launches_per_iter,
-            'e2e': {'value': units * K / e2e_info['seconds'], 'unit': 'frame*person*iter/s', 'h2d_bytes_per_step': h2d / K, 'd2h_bytes_per_step': d2h / K,
-                    'what': f'GlobalReconOptimizer.optimize(in_dict numpy)->numpy dict incl. init_data, {K} iterations', **e2e_info},
-            'roofline': {'bound': 'hbm', 'kernel': 'LBS of the iteration: lbs_blend_tc_kernel (+ feature kernel) + lbs_skin_tc_kernel', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+        hbm_roofline = {'bound': 'hbm', 'kernel': 'LBS of the iteration: lbs_blend_tc_kernel (+ feature kernel) + lbs_skin_tc_kernel', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                          'traffic': NCU_LBS_DRAM_BYTES.get(n_local), 'traffic_source': 'profiles/ (ncu --set full, dram__bytes_read + write, per launch)' if n_local in NCU_LBS_DRAM_BYTES else None,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes': alg_bytes, 'kernel_ms': lbs_ms, 'kernel_share_of_step': lbs_ms / cold_ms,
@@ -669,7 +653,45 @@ def run_ours(args):
                          'fp32': {'achieved_tflops': fp32_tf, 'executed_tflops': fp32_exec, 'peak_tflops': fp32_peak, 'frac': fp32_tf / fp32_peak, 'frac_executed': fp32_exec / fp32_peak,
                                   'peak_source': 'glamr_fp32_probe: register-resident FFMA loop timed in this run (best of 5)',
                                   'note': 'algorithmic LBS flops (15.85 MFLOP per frame-person, dense skinning) over the LBS time (blend GEMM timed in situ on its side stream + skinning kernel) against the measured FP32 FFMA peak; '
-                                          'both LBS kernels run on the tensor cores now (3xTF32: roofline.tensor is the blend; the skinning is a K = 24 GEMM whose time is its TMEM epilogue and operand loads), so this FP32-FMA fraction is a comparison figure against the round-1 SIMT kernel, not a bound; the HBM fraction is small by construction (constants stay L2-resident)'}},
+                                          'both LBS kernels run on the tensor cores now (3xTF32: the top-level roofline is the blend; the skinning is a K = 24 GEMM whose time is its TMEM epilogue and operand loads), so this FP32-FMA fraction is a comparison figure against the round-1 SIMT kernel, not a bound; the HBM fraction is small by construction (constants stay L2-resident)'}}
+        tensor = hbm_roofline.pop('tensor')
+        if tensor is not None:
+            # the dominant kernel of the iteration is the tensor-core blend GEMM: quote the roofline against the tensor pipe.  Algorithmic flops =
+            # the blend contraction of lbs.py:240,256-267 (207 pose features + 10 betas per vertex coordinate; the template is an add):
+            # 2 x 217 x 20670 per frame-person -- the share of SURVEY 8(d)'s 15.85 MFLOP that this kernel computes.  The kernel ISSUES 3x that
+            # (3xTF32) on padded tiles: issued_* below.
+            alg_flops = 2.0 * 217 * 20670 * n_local
+            tf32_peak = tensor['peak_tflops_tf32']
+            ach = alg_flops / (tensor['kernel_ms'] * 1e-3) / 1e12
+            roofline = {'bound': 'tensor', 'kernel': 'lbs_blend_tc_kernel (+ blend_features_kernel): the longest kernel of the iteration, launched alone (warm L2)',
+                        'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak,
+                        'traffic': NCU_BLEND_DRAM_BYTES.get(n_local), 'traffic_source': 'profiles/lbs_tc_kernels_r02_final.md (ncu --set full, dram read + write of the blend kernel, cold)' if n_local in NCU_BLEND_DRAM_BYTES else None,
+                        'peak_source': ('MEASURED_PEAKS.json bf16_tflops / 2' if 'bf16_tflops' in peaks else 'fallback: nominal 2250 / 2') + ' = dense TF32',
+                        'algorithmic_flops': alg_flops, 'kernel_ms': tensor['kernel_ms'],
+                        'issued_tflops_tf32': tensor['achieved_tflops_tf32'], 'issued_frac': tensor['frac'],
+                        'note': 'frac = algorithmic blend flops / time / dense TF32 peak; issued_frac counts the three kind::tf32 MMAs per product (3xTF32) on 128 x 256 tiles '
+                                '(ncu: tensor pipe active 48 % of the cycles at 300 frames, 0.71 of peak issue at 1200 frames, profiles/chain_analysis_r02.md)',
+                        'hbm': hbm_roofline, 'fp32': hbm_roofline.pop('fp32'), 'kernel_parts': hbm_roofline.pop('kernel_parts')}
+        else:
+            roofline = hbm_roofline
+        res = {
+            'metric': 'global_opt_frame_person_iterations_per_sec', 'value': units / (cold_ms * 1e-3), 'unit': 'frame*person*iter/s',
+            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': cold_ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'iters_per_sec': 1e3 / cold_ms,
+            'value_l2_warm': units / (warm_ms * 1e-3), 'ms_per_step_l2_warm': warm_ms,
+            'config': {'workload': f'{CFG_ID}:init_opt, {persons} person(s) x {args.frames} frames, full-LBS every iteration',
+                       'persons': persons, 'frames': args.frames,
+                       'parallelism': (f'frame-persons sharded over {world} GPU(s), ' + ('gradient reduction over NVLink peer memory fused into the Adam kernel' if peer else '1 NCCL allreduce/iter')) if world > 1 else 'single GPU',
+                       'l2': 'flushed between timed iterations (256 MiB fill); value_l2_warm = back-to-back replays',
+                       'cuda_graph': graph_on, 'prior': 'CUDA infiller+traj-pred with seeded stand-in weights (no checkpoints offline), latents injected',
+                       'env': {k: os.environ.get(k) for k in ECHO_ENV if os.environ.get(k) is not None}},
+            'clocks': clocks,
+            'gpu_launches': launches_per_iter * K,
+            'gpu_launches_per_step': launches_per_iter,
+            'e2e': {'value': units * K / e2e_info['seconds'], 'unit': 'frame*person*iter/s', 'h2d_bytes_per_step': h2d / K, 'd2h_bytes_per_step': d2h / K,
+                    'what': f'GlobalReconOptimizer.optimize(in_dict numpy)->numpy dict incl. init_data, {K} iterations', **e2e_info},
+            'roofline': roofline,
             'extras': extras,
         }
         if parity is not None:
