@@ -126,6 +126,48 @@ def host_threads():
     return max(1, len(os.sched_getaffinity(0)))
 
 
+class CpuLegTimeout(Exception):
+    pass
+
+
+class wall_clock_limit:
+    """Hard wall-clock bound for a CPU leg of the bench (the oracle port is thousands of small torch CPU ops per iteration, so a
+    SIGALRM handler gets to run between two of them).  On hosts that are shared with other jobs a many-thread torch CPU
+    iteration has been seen to take from 4 s to minutes; without a bound one such iteration decides how long bench.py runs."""
+
+    pool = None          # seconds all CPU legs of this process may still spend together (None: no shared budget)
+
+    def __init__(self, seconds):
+        self.seconds = max(1, int(seconds))
+
+    def _fire(self, signum, frame):
+        raise CpuLegTimeout(f'CPU leg exceeded {self.seconds} s')
+
+    def __enter__(self):
+        import signal
+        import threading
+        cls = wall_clock_limit
+        if cls.pool is not None:
+            if cls.pool < 2.0:
+                raise CpuLegTimeout('the CPU-time budget of this bench run is spent')
+            self.seconds = max(1, min(self.seconds, int(cls.pool)))
+        self.t0 = time.perf_counter()
+        self.active = threading.current_thread() is threading.main_thread()
+        if self.active:
+            self.old = signal.signal(signal.SIGALRM, self._fire)
+            signal.alarm(self.seconds)
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            import signal
+            signal.alarm(0)
+            signal.signal(signal.SIGALRM, self.old)
+        if wall_clock_limit.pool is not None:
+            wall_clock_limit.pool -= time.perf_counter() - self.t0
+        return False
+
+
 class CpuPort:
     """the oracle port (torch CPU) set up on one workload; `time_iterations` runs optimize_main of one stage and returns the
     per-iteration seconds.  Timing protocol: thread-count sweep, warm-up discarded, >= 20 timed iterations,
@@ -151,51 +193,84 @@ class CpuPort:
         if threads is not None:
             self.torch.set_num_threads(threads)
         times = []
+        self._times = times                      # readable by a caller whose wall-clock limit interrupts the loop
         sp = self.specs
         self.model.optimize_main(self.data, sp['opt_variables'], sp['opt_lr'], n, sp['loss_cfg'], {'stage': self.stage},
                                  on_iter=lambda it, last, dt: times.append(dt))
         return times
 
     def sweep_threads(self, warm=1, probe=3, budget_s=40.0):
-        """median seconds per iteration for each candidate thread count, smallest count first; a candidate is abandoned as soon
-        as one of its iterations takes > 3x the best median so far, and the sweep stops when `budget_s` is spent (boxes exist
-        where many-thread torch CPU runs are 25x slower than 8 threads).  -> (best_threads, {threads: median})"""
-        cands = sorted({t for t in (8, 16, 32, host_threads()) if t <= host_threads()})
-        res, t_start = {}, time.perf_counter()
+        """median seconds per iteration for each candidate thread count, smallest count first.  Bounded three ways (boxes exist
+        where many-thread torch CPU runs are 25-250x slower than 8 threads, and hosts shared with other jobs where they take
+        minutes): the all-threads candidate only runs on hosts with <= 64 threads (128 threads measured 4.5 - 12 s per iteration
+        against 45 - 100 ms at 16 - 32, profiles/README_r02.md); a candidate is abandoned as soon as one of its iterations takes
+        > 3x the best median so far; the sweep stops when a candidate is slower than the one before it (the scaling has turned
+        over), when `budget_s` is spent, or when a candidate hits its own wall-clock limit.  -> (best_threads, {threads: median})"""
+        cands = sorted({t for t in (8, 16, 32) if t <= host_threads()} | ({host_threads()} if host_threads() <= 64 else set()))
+        res, t_start, prev = {}, time.perf_counter(), None
         for t in cands:
-            if res and time.perf_counter() - t_start > budget_s:
+            left = budget_s - (time.perf_counter() - t_start)
+            if res and left <= 0:
                 break
             ts = []
-            for i in range(warm + probe):
-                (dt,) = self.time_iterations(1, threads=t)
-                ts.append(dt)
-                if res and dt > 3.0 * min(res.values()):
+            try:
+                with wall_clock_limit(max(10.0, left) if res else 120.0):
+                    for i in range(warm + probe):
+                        (dt,) = self.time_iterations(1, threads=t)
+                        ts.append(dt)
+                        if res and dt > 3.0 * min(res.values()):
+                            break
+            except CpuLegTimeout:
+                if not ts and not res:
+                    raise
+                if not ts:
                     break
             res[t] = float(np.median(ts[warm:] or ts))
+            if prev is not None and res[t] > 1.25 * prev:
+                break
+            prev = res[t]
         best = min(res, key=res.get)
         return best, res
 
 
 def cpu_baseline_block(assets, in_dict, cfg, units, iters, stage=None, sweep=True, threads=None, budget_s=60.0):
     """the CPU port on one workload, bounded by wall-clock: thread sweep (<= 40 s), then min(iters, what fits `budget_s`) timed
-    iterations but never fewer than 5"""
-    port = CpuPort(assets, in_dict, cfg, stage)
-    port.time_iterations(1, threads=threads or min(8, host_threads()))       # first-call warm-up (allocator, thread pool)
-    if sweep:
-        threads, sweep_res = port.sweep_threads()
-        per = sweep_res[threads]
-    else:
-        threads, sweep_res = threads or min(8, host_threads()), {}
-        (per,) = port.time_iterations(1, threads=threads)
+    iterations but never fewer than 5; every part runs under a hard wall-clock limit and the block degrades to what it has
+    measured (or to a 'skipped' note) instead of stalling the bench on a host that is busy with other jobs"""
+    t_block = time.perf_counter()
+    try:
+        with wall_clock_limit(120):
+            port = CpuPort(assets, in_dict, cfg, stage)
+            port.time_iterations(1, threads=threads or min(8, host_threads()))       # first-call warm-up (allocator, thread pool)
+        if sweep:
+            threads, sweep_res = port.sweep_threads()
+            per = sweep_res[threads]
+        else:
+            threads, sweep_res = threads or min(8, host_threads()), {}
+            with wall_clock_limit(90):
+                (per,) = port.time_iterations(1, threads=threads)
+    except CpuLegTimeout as e:
+        return {'skipped': f'{e} during set-up / thread sweep (host busy); see --impl reference', 'kind': 'port', 'seconds_spent': time.perf_counter() - t_block}
     n = int(max(5, min(iters, budget_s / max(per, 1e-6))))
-    ts = port.time_iterations(n, threads=threads)
+    ts, cut = [], False
+    try:
+        with wall_clock_limit(max(3.0 * budget_s, 8.0 * per * 5)):
+            port.torch.set_num_threads(threads)
+            sp = port.specs
+            port.model.optimize_main(port.data, sp['opt_variables'], sp['opt_lr'], n, sp['loss_cfg'], {'stage': port.stage},
+                                     on_iter=lambda it, last, dt: ts.append(dt))
+    except CpuLegTimeout:
+        cut = True
+    if not ts:
+        ts = [per]
     med, best = float(np.median(ts)), float(np.min(ts))
     return {'value': units / med, 'value_best': units / best, 'unit': 'frame*person*iter/s', 'cores': threads, 'host_threads_available': host_threads(),
             'kind': 'port', 'ms_per_iter_median': med * 1e3, 'ms_per_iter_best': best * 1e3,
             'thread_sweep_ms_per_iter': {str(k): round(v * 1e3, 2) for k, v in sweep_res.items()},
             'ms_per_iter_list': [round(t * 1e3, 1) for t in ts],
-            'sample': f'{n} timed iterations (median; best in value_best) of the oracle port (torch CPU, {threads} threads' +
-                      (' = fastest of the sweep' if sweep else '') + f') on the same workload ({port.stage}), after warm-up; bounded to ~{budget_s:.0f} s'}
+            'sample': f'{len(ts)} timed iterations (median; best in value_best) of the oracle port (torch CPU, {threads} threads' +
+                      (' = fastest of the sweep' if sweep else '') + f') on the same workload ({port.stage}), after warm-up; bounded to ~{budget_s:.0f} s' +
+                      (' (cut by the wall-clock limit)' if cut else '')}
 
 
 def run_reference(args):
@@ -210,8 +285,9 @@ def run_reference(args):
     # loops over persons, its cost per frame-person is the same) and the metric counts those units; if one person is still
     # too slow, fewer timed steps run (stated in `sample`).
     sample = persons
-    port = CpuPort(assets, in_dict, cfg)
-    port.time_iterations(1, threads=min(8, host_threads()))
+    with wall_clock_limit(180):
+        port = CpuPort(assets, in_dict, cfg)
+        port.time_iterations(1, threads=min(8, host_threads()))
     threads, sweep_res = port.sweep_threads(warm=1, probe=3)
     probe = sweep_res[threads]
     if probe * (K + W) > REF_BUDGET_S and persons > 1:
@@ -221,7 +297,13 @@ def run_reference(args):
     k_run = K
     if probe * sample / persons * (K + W) > REF_BUDGET_S:
         k_run = max(20, int(REF_BUDGET_S / (probe * sample / persons)) - W)
-    ts = port.time_iterations(W + k_run, threads=threads)[W:]
+    cut = False
+    try:
+        with wall_clock_limit(2.5 * REF_BUDGET_S):
+            ts = port.time_iterations(W + k_run, threads=threads)[W:]
+    except CpuLegTimeout:                        # host busy with other jobs: report what was timed
+        ts, cut = list(port._times[W:]) or [probe * sample / persons], True
+        k_run = len(ts)
     med, best = float(np.median(ts)), float(np.min(ts))
     units = sample * args.frames
     val = units / med
@@ -236,7 +318,7 @@ def run_reference(args):
                          'kind': 'port', 'thread_sweep_ms_per_iter': {str(k): round(v * 1e3, 2) for k, v in sweep_res.items()},
                          'ms_per_iter_list': [round(t * 1e3, 1) for t in ts],
                          'sample': f'{k_run} timed iterations (median; best in value_best) after {W} warm-up of the oracle port (torch CPU, {threads} threads = '
-                                   f'fastest of the sweep), each over {sample} of the {persons} person(s) x {args.frames} frames'},
+                                   f'fastest of the sweep), each over {sample} of the {persons} person(s) x {args.frames} frames' + (' (cut by the wall-clock limit)' if cut else '')},
         'e2e': {'value': val, 'unit': 'frame*person*iter/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(out))
@@ -502,7 +584,13 @@ def staged_workload(ctx, cfg_id, persons, frames, K, with_e2e=True, cpu_iters=0,
         res['e2e'] = {'value': units * info['iterations'] / info['seconds'], 'unit': 'frame*person*iter/s', **info,
                       'h2d_bytes': h2d, 'd2h_bytes': d2h, 'what': 'optimize(in_dict numpy) -> numpy dict incl. init_data, all YAML iterations of both stages'}
     if cpu_iters and ctx.rank == 0 and ctx.world == 1:
+        # this leg may use at most a third of the run's CPU budget: the headline workload's leg comes last
+        pool0 = wall_clock_limit.pool
+        if pool0 is not None:
+            wall_clock_limit.pool = pool0 / 3.0
         res['cpu_baseline'] = cpu_baseline_block(assets, in_dict, cfg, units, cpu_iters, stage=last, sweep=False, threads=cpu_threads, budget_s=30.0)
+        if pool0 is not None:
+            wall_clock_limit.pool = pool0 - (pool0 / 3.0 - wall_clock_limit.pool)
     return res
 
 
@@ -568,6 +656,8 @@ def c5_sweep(ctx, n_seq=32, frames=300):
 
 def run_ours(args):
     refuse_experiment_switches()
+    # all CPU legs of this run (main cpu_baseline + the north-star one) share one wall-clock budget: the GPU numbers must not wait for a busy host
+    wall_clock_limit.pool = float(os.environ.get('GLAMR_CPU_BUDGET_S', 180.0))
     ctx = Ctx()
     torch, world, rank = ctx.torch, ctx.world, ctx.rank
     persons = args.persons or world
