@@ -38,6 +38,10 @@ BYTES_CONST = 19_595_160          # SMPL constants, fp32 dense
 BYTES_PER_FP = 1_460              # per frame-person reads + gradient writes + Adam traffic
 FLOPS_PER_FP = 15.85e6            # dense full-LBS forward (algorithmic)
 FLOPS_PER_FP_EXECUTED = 9.8e6     # K-sparse skinning (4 weights per vertex): what the kernel really issues
+T_START = time.perf_counter()
+# soft wall-clock budget of one `python bench.py` (our arm): the keyed extras (north star, C4, C3, C5) are skipped, with a note, once 60 % of it
+# is spent, so that the headline line is always printed within minutes even on a host that is busy with other jobs
+BENCH_BUDGET_S = float(os.environ.get('GLAMR_BENCH_BUDGET_S', 480.0))
 REF_BUDGET_S = float(os.environ.get('GLAMR_REF_BUDGET_S', 150.0))   # wall-clock bound (s) of the CPU reference arm (--impl reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of one LBS launch, keyed by frame-persons per launch (ncu capture, profiles/)
 NCU_BLEND_DRAM_BYTES = {300: 37911808 + 2394624}               # lbs_blend_tc_kernel alone
@@ -697,18 +701,25 @@ def run_ours(args):
     want = ALL_EXTRAS if args.extras == 'all' else ([] if args.extras == 'none' else args.extras.split(','))
     extras = {}
     Kx = min(K, 100)
-    if 'north_star' in want:
+    def in_budget(name):
+        """same decision on every rank (the extras contain collectives)"""
+        (el,) = ctx.max_over_ranks(time.perf_counter() - T_START)
+        if el > 0.6 * BENCH_BUDGET_S:
+            extras[name] = {'skipped': f'{el:.0f} s of the {BENCH_BUDGET_S:.0f} s bench budget were spent before this extra (busy host); run `python bench.py --extras {name}`'}
+            return False
+        return True
+    if 'north_star' in want and in_budget('north_star'):
         extras['north_star'] = staged_workload(ctx, 'glamr_static_multi', 4, 300, Kx, cpu_iters=0 if args.no_cpu_baseline else 8)
         _dbg('north_star done')
-    if 'c4' in want:
+    if 'c4' in want and in_budget('c4'):
         extras['c4'] = staged_workload(ctx, 'glamr_static_multi', 8, 500, min(Kx, 50), with_e2e=False)
         _dbg('c4 done')
-    if 'c3' in want:
+    if 'c3' in want and in_budget('c3'):
         r = c3_prior(ctx)
         if rank == 0:
             extras['c3'] = r
         _dbg('c3 done')
-    if 'c5' in want:
+    if 'c5' in want and in_budget('c5'):
         extras['c5'] = c5_sweep(ctx)
         _dbg('c5 done')
 
@@ -788,6 +799,8 @@ def run_ours(args):
             res['parity'] = parity
             bad = not parity['ok']
         if world == 1 and not args.no_cpu_baseline:
+            left = BENCH_BUDGET_S - (time.perf_counter() - T_START)
+            wall_clock_limit.pool = max(25.0, min(wall_clock_limit.pool if wall_clock_limit.pool is not None else 180.0, left))
             res['cpu_baseline'] = cpu_baseline_block(assets, in_dict, cfg, units, args.cpu_sample_iters)
         elif world > 1:
             res['cpu_baseline'] = {'skipped': 'N > 1: the reference arm (--impl reference) times the CPU path; rank 0 does not stall the other GPUs'}
